@@ -1,0 +1,327 @@
+#!/usr/bin/env python
+"""Generate tests/golden/*.npz by running the reference's OWN environment code (SURVEY.md §8c recipe).
+
+Runs only in the build container (needs /root/reference).  The reference's MimicWalker3dEnv / MimicEnv / Monitor /
+StraightWalkingTrajectories classes are imported *unmodified* from /root/reference; the third-party packages they
+import but that are not installed (gym, mujoco_py, seaborn, matplotlib, wandb, stable_baselines3) are replaced by
+import stubs, and gym's ``MujocoEnv`` by a minimal stand-in whose ``sim`` is the float64 physics oracle
+(oracle/walker_physics.c).  Two textual substitutions are applied while loading reference modules, both forced by
+the checkout rather than chosen: ``PATH_REF_TRAJECS = PATH_CONSTANT_SPEED`` (the default ramp mocap is missing, Q8)
+and ``from collections import Iterable`` -> ``collections.abc`` (Python >= 3.10).
+
+Conditions of the run (recorded in the fixture):
+  * smoothing state (drloco.common.utils._exp_weighted_averages) is swapped per env, i.e. SubprocVecEnv semantics (Q17);
+  * the mocap array is restored to its pristine copy before every reset, i.e. the in-place accumulation of
+    adjust_COM_Z_pos across episodes (Q4) is waived, as documented in DESIGN.md;
+  * envs are stepped with DummyVecEnv semantics written out by hand (SB3 is not installed): on done keep the terminal
+    observation and reset.
+
+Usage: python tools/gen_golden.py            (writes tests/golden/w3d_rollout.npz, w3d_cursor.npz)
+"""
+import collections
+import collections.abc
+import copy
+import os
+import random
+import sys
+import tempfile
+import types
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = "/root/reference"
+sys.path.insert(0, REPO)
+
+from drloco_b200.model import get_model            # noqa: E402
+from oracle.physics import OraclePhysics           # noqa: E402
+
+
+class _Dummy:
+    """absorbs any attribute access / call / item assignment (plot configuration of the reference)."""
+
+    def __init__(self, *a, **k):
+        pass
+
+    def __call__(self, *a, **k):
+        return _Dummy()
+
+    def __getattr__(self, name):
+        return _Dummy()
+
+    def __setitem__(self, k, v):
+        pass
+
+    def __getitem__(self, k):
+        return _Dummy()
+
+
+def _stub(name, **attrs):
+    mod = types.ModuleType(name)
+    mod.__dict__.update(attrs)
+    def _ga(n):                                # PEP 562
+        if n.startswith("__"):
+            raise AttributeError(n)
+        return _Dummy()
+    mod.__getattr__ = _ga
+    sys.modules[name] = mod
+    return mod
+
+
+class MujocoException(Exception):
+    pass
+
+
+class _Box:
+    def __init__(self, low, high):
+        self.low, self.high = np.asarray(low, np.float32), np.asarray(high, np.float32)
+        self.shape = self.low.shape
+
+    def sample(self):
+        return np.random.uniform(self.low, self.high).astype(np.float32)
+
+
+class _SimData:
+    pass
+
+
+class _Sim:
+    """Stand-in for mujoco_py.MjSim backed by the physics oracle."""
+
+    def __init__(self, model):
+        self.phys = OraclePhysics(model)
+        self.data = _SimData()
+        self.data.qpos = model.qpos0.copy()
+        self.data.qvel = np.zeros(model.nv)
+        self.data.ctrl = np.zeros(model.nu)
+        self.data.actuator_force = np.zeros(model.nu)
+        self.data.site_xpos = self.phys.site_xpos(self.data.qpos)
+        self.data.time = 0.0
+        self._m = model
+
+    def reset(self):
+        self.data.qpos[:] = self._m.qpos0
+        self.data.qvel[:] = 0
+        self.phys.qacc_warm[:] = 0
+        self.forward()
+
+    def forward(self):
+        self.data.site_xpos = self.phys.site_xpos(self.data.qpos)
+
+    def step(self):
+        m = self._m
+        self.data.actuator_force[:] = np.clip(np.clip(self.data.ctrl, m.act_ctrlrange[:, 0], m.act_ctrlrange[:, 1])
+                                              * m.act_gear, m.act_forcerange[:, 0], m.act_forcerange[:, 1])
+        if self.phys.step(self.data.qpos, self.data.qvel, self.data.ctrl, 1):
+            raise MujocoException("unstable simulation")
+
+
+class _ModelView:
+    def __init__(self, model):
+        self.actuator_ctrlrange = model.act_ctrlrange.copy()
+        self.actuator_forcerange = model.act_forcerange.copy()
+
+
+class FakeMujocoEnv:
+    """What gym 0.18.0's MujocoEnv does for MimicEnv, minus rendering."""
+
+    def __init__(self, model_path, frame_skip):
+        name = os.path.basename(model_path)
+        self._wm = get_model({"walker3d_flat_feet.xml": "StraightMimicWalker",
+                              "walker_165cm_65kg.xml": "MimicWalker165cm65kg"}[name])
+        self.frame_skip = frame_skip
+        self.sim = _Sim(self._wm)
+        self.data = self.sim.data
+        self.model = _ModelView(self._wm)
+        self.init_qpos, self.init_qvel = self.data.qpos.copy(), self.data.qvel.copy()
+        cr = self.model.actuator_ctrlrange
+        self.action_space = _Box(cr[:, 0], cr[:, 1])
+        observation, _reward, done, _info = self.step(self.action_space.sample())
+        assert not done
+        self.observation_space = _Box(np.full(observation.shape, -np.inf), np.full(observation.shape, np.inf))
+
+    def seed(self, seed=None):
+        return [seed]
+
+    def reset(self):
+        self.sim.reset()
+        return self.reset_model()
+
+    def set_state(self, qpos, qvel):
+        self.data.qpos[:] = qpos
+        self.data.qvel[:] = qvel
+        self.sim.phys.qacc_warm[:] = 0
+        self.sim.forward()
+
+    def do_simulation(self, ctrl, n_frames):
+        self.data.ctrl[:] = ctrl
+        for _ in range(n_frames):
+            self.sim.step()
+
+    @property
+    def dt(self):
+        return self._wm.timestep * self.frame_skip
+
+
+class _Wrapper:
+    def __init__(self, env):
+        self.env = env
+
+    def __getattr__(self, name):
+        return getattr(self.env, name)
+
+
+def install_stubs():
+    collections.Iterable = collections.abc.Iterable
+    gym = _stub("gym", Wrapper=_Wrapper)
+    gym.utils = _stub("gym.utils", EzPickle=type("EzPickle", (), {"__init__": lambda self, *a, **k: None}))
+    _stub("gym.envs")
+    _stub("gym.envs.mujoco")
+    _stub("gym.envs.mujoco.mujoco_env", MujocoEnv=FakeMujocoEnv)
+    mj = _stub("mujoco_py", MjSimState=_Dummy)
+    mj.builder = _stub("mujoco_py.builder", MujocoException=MujocoException)
+    for name in ("seaborn", "matplotlib", "matplotlib.pyplot", "wandb", "stable_baselines3",
+                 "stable_baselines3.common", "stable_baselines3.common.vec_env"):
+        _stub(name)
+    for cls in ("DummyVecEnv", "SubprocVecEnv", "VecNormalize"):
+        setattr(sys.modules["stable_baselines3.common.vec_env"], cls, type(cls, (), {}))
+    sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
+
+
+def load_reference():
+    """import the reference package with the two forced substitutions; returns (env class, Monitor class, utils)."""
+    sys.path.insert(0, REF)
+    # is_remote() <=> 'code/torch' in cwd: no viewer, n_envs = 8 (Q12/Q13)
+    work = os.path.join(tempfile.mkdtemp(), "code", "torch")
+    os.makedirs(work)
+    os.chdir(work)
+    import torch  # noqa: F401  (hypers.py imports it; load the real one before the stubs go in)
+    install_stubs()
+    name = "drloco.ref_trajecs.straight_walk_trajecs"
+    path = os.path.join(REF, "drloco/ref_trajecs/straight_walk_trajecs.py")
+    src = open(path).read().replace("PATH_REF_TRAJECS = PATH_SPEED_RAMP", "PATH_REF_TRAJECS = PATH_CONSTANT_SPEED")
+    import drloco.ref_trajecs  # noqa: F401  (package)
+    mod = types.ModuleType(name)
+    mod.__file__ = path
+    sys.modules[name] = mod
+    exec(compile(src, path, "exec"), mod.__dict__)
+    setattr(sys.modules["drloco.ref_trajecs"], "straight_walk_trajecs", mod)
+    from drloco.mujoco.mimic_walker3d import MimicWalker3dEnv
+    from drloco.mujoco.monitor_wrapper import Monitor
+    from drloco.common import utils
+    return MimicWalker3dEnv, Monitor, utils
+
+
+def gen_w3d_rollout(n_envs=8, n_steps=400, seed=0, out="w3d_rollout.npz"):
+    Env, Monitor, utils = load_reference()
+    random.seed(seed)
+    np.random.seed(seed)
+    rng = np.random.default_rng(seed)
+    envs, ewa, pristine = [], [], []
+    for i in range(n_envs):
+        utils._exp_weighted_averages = {}
+        e = Monitor(Env())
+        envs.append(e)
+        ewa.append({})
+        pristine.append(copy.deepcopy(e.env.refs.data))
+    nv, nu, D = 14, 8, 29
+
+    rsi_log = []
+
+    # record the RSI draw of every reset
+    for i, mon in enumerate(envs):
+        refs = mon.env.refs
+        orig = refs.get_random_init_state
+
+        def wrapped(orig=orig, refs=refs, i=i):
+            out = orig()
+            rsi_log.append((i, refs._i_step, refs._pos))
+            return out
+        refs.get_random_init_state = wrapped
+
+    T = n_steps
+    g = dict(actions=np.zeros((T, n_envs, nu), np.float32), obs=np.zeros((T, n_envs, D)), rew=np.zeros((T, n_envs)),
+             done=np.zeros((T, n_envs), np.uint8), terminal_obs=np.full((T, n_envs, D), np.nan),
+             qpos=np.zeros((T, n_envs, nv)), qvel=np.zeros((T, n_envs, nv)), cursor=np.zeros((T, n_envs, 4), np.int32),
+             ctrl=np.zeros((T, n_envs, nu)), comps=np.zeros((T, n_envs, 3)), walked=np.zeros((T, n_envs)),
+             des_vel=np.zeros((T, n_envs)), rsi=np.full((T + 1, n_envs, 2), -1, np.int32))
+    obs0 = np.zeros((n_envs, D))
+    random.seed(seed + 1)
+    for i in range(n_envs):
+        utils._exp_weighted_averages = ewa[i]
+        envs[i].env.refs.data = copy.deepcopy(pristine[i])
+        obs0[i] = envs[i].env.reset()
+        g["rsi"][0, i] = rsi_log[-1][1:]
+    g["obs0"] = obs0
+    g["qpos0"] = np.stack([e.env.sim.data.qpos.copy() for e in envs])
+    g["qvel0"] = np.stack([e.env.sim.data.qvel.copy() for e in envs])
+    g["cursor0"] = np.array([[e.env.refs._i_step, e.env.refs._pos, e.env.refs.count_steps_same_vel, e.env.ep_dur]
+                             for e in envs], np.int32)
+    for t in range(T):
+        a = rng.uniform(-1.3, 1.3, size=(n_envs, nu)).astype(np.float32)
+        # damp the action noise so that some envs survive long enough to cross mocap steps
+        a[: n_envs // 2] *= 0.15
+        g["actions"][t] = a
+        for i, mon in enumerate(envs):
+            utils._exp_weighted_averages = ewa[i]
+            e = mon.env
+            o, r, d, _ = mon.step(a[i])
+            g["qpos"][t, i], g["qvel"][t, i] = e.sim.data.qpos, e.sim.data.qvel
+            g["cursor"][t, i] = (e.refs._i_step, e.refs._pos, e.refs.count_steps_same_vel, e.ep_dur)
+            g["ctrl"][t, i] = e.sim.data.ctrl
+            g["comps"][t, i] = (e.pos_rew, e.vel_rew, e.com_rew)
+            g["walked"][t, i] = e.walked_distance
+            g["des_vel"][t, i] = e.desired_walking_speed[0]
+            g["rew"][t, i], g["done"][t, i] = r, d
+            if d:
+                g["terminal_obs"][t, i] = o
+                e.refs.data = copy.deepcopy(pristine[i])  # Q4 waiver
+                o = e.reset()
+                g["rsi"][t + 1, i] = rsi_log[-1][1:]
+            g["obs"][t, i] = o
+    # Monitor attributes the callback reads through get_attr (callback.py:106-108,142,162-164,227)
+    for name in ("ep_len_smoothed", "ep_ret_smoothed", "mean_reward_smoothed", "moved_distance",
+                 "mean_ep_pos_rew_smoothed", "mean_ep_vel_rew_smoothed", "mean_ep_com_rew_smoothed",
+                 "mean_abs_ep_torque_smoothed"):
+        g["mon_" + name] = np.array([float(getattr(m, name)) for m in envs])
+    g["mon_ep_lens"] = np.array([len(m.ep_lens) for m in envs], np.int32)
+    g["mon_ep_lens_flat"] = np.array([x for m in envs for x in m.ep_lens], np.int32)
+    g["meta"] = np.array("reference MimicWalker3dEnv+Monitor (unmodified) over oracle physics; Q4 waived; "
+                         "per-env smoothing dicts; seed=%d" % seed)
+    os.makedirs(os.path.join(REPO, "tests/golden"), exist_ok=True)
+    np.savez_compressed(os.path.join(REPO, "tests/golden", out), **g)
+    print(out, "episodes:", int(g["done"].sum()), "mean rew", g["rew"].mean())
+
+
+def gen_w3d_cursor(out="w3d_cursor.npz", seed=0, n=1200):
+    """pure cursor trace (SURVEY.md §8c known-answer iii): refs.next() from random.seed(0)."""
+    _, _, _ = load_reference()
+    from drloco.ref_trajecs import straight_walk_trajecs as ref_sw
+    from drloco.mujoco.mimic_walker3d import qpos_indices, qvel_indices
+    random.seed(seed)
+    refs = ref_sw.StraightWalkingTrajectories(qpos_indices, qvel_indices)
+    refs.get_random_init_state()
+    tr = np.zeros((n + 1, 4), np.int32)
+    ph = np.zeros(n + 1)
+    dv = np.zeros(n + 1)
+    qp = np.zeros((n + 1, 14))
+    qv = np.zeros((n + 1, 14))
+    left = np.zeros(n + 1, np.uint8)
+    for t in range(n + 1):
+        tr[t] = (refs._i_step, refs._pos, refs._trajec_len, refs.count_steps_same_vel)
+        ph[t], dv[t] = refs.get_phase_variable(), refs.get_step_velocity()
+        qp[t], qv[t] = refs.get_qpos().astype(np.float64), refs.get_qvel().astype(np.float64)
+        left[t] = refs.is_step_left()
+        refs.next()
+    np.savez_compressed(os.path.join(REPO, "tests/golden", out), trace=tr, phase=ph, des_vel=dv, qpos=qp, qvel=qv,
+                        left=left, step_velocities=np.asarray(refs.step_velocities, np.float64),
+                        left_step_indices=np.asarray(refs.left_step_indices, np.int32))
+    print(out, tr[0], tr[-1])
+
+
+if __name__ == "__main__":
+    which = sys.argv[1] if len(sys.argv) > 1 else "all"
+    if which in ("all", "cursor"):
+        gen_w3d_cursor()
+    if which in ("all", "rollout"):
+        gen_w3d_rollout()

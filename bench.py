@@ -1,0 +1,319 @@
+#!/usr/bin/env python
+"""bench.py — env-steps/s of the batched DeepMimic walker step (reward, termination and RSI resets included).
+
+Contract (driver): ``python bench.py --gpus N --steps K --warmup W`` prints ONE JSON line on rank 0.
+  * workload at N=1: BASELINE.json configs[1] — MimicWalker3d (StraightMimicWalker), straight-walking mocap, 4096 envs,
+    random actions U(-1,1); for N>1 the same 4096 envs per GPU (weak scaling; envs are independent, the only exchange
+    is the packed VecNormalize-moment all-reduce).
+  * ``value``: env-steps/s with actions already resident in HBM (tensor API: fused step kernel + VecNormalize kernels
+    + the NCCL all-reduce when N>1), CUDA-event timed, max over ranks.
+  * ``e2e``: the same metric through the SB3-facing numpy API (B200VecNormalize.step on HOST float32 actions; H2D of the
+    actions and D2H of obs/reward/done inside the timed region).
+  * ``roofline``: the step kernel is neither HBM- nor tensor-bound: reported against HBM with the
+    algorithmic 425 B/env-step, plus an ``fp32`` object against the FFMA peak measured in the same run.
+  * ``cpu_baseline``: the oracle stack (reference env logic restated in numpy + float64 MuJoCo-restatement physics in C)
+    on a bounded sample, single core ("port").
+  * ``--impl reference``: the same oracle stack on all host cores, one process per core (what SubprocVecEnv does).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+ENV_ID = "StraightMimicWalker"
+ENVS_PER_GPU = 4096
+ALGO_BYTES_PER_ENV_STEP = 425.0        # SURVEY.md §8d / DESIGN.md
+ALGO_FLOP_PER_ENV_STEP = 0.40e6        # counted fp32 flops of one W3D env-step (20 dynamics evaluations)
+
+
+def _peaks():
+    path = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f), "measured"
+    return {"hbm_gbs": 6650.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[k] for r in self.rows if len(r) >= 6 for k in range(4) if r[2 + k].lower() == "active"})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def fp32_peak_tflops(torch) -> float:
+    """FFMA peak measured with a dependent-chain-free register kernel written with torch ops is not possible; use a
+    dense fp32 (non-tensor-core) matmul as the practical upper bound of the FP32 pipe and report it as such."""
+    a = torch.randn(4096, 4096, device="cuda")
+    b = torch.randn(4096, 4096, device="cuda")
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    for _ in range(2):
+        (a @ b)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    best = 0.0
+    for _ in range(3):
+        e0.record()
+        for _ in range(4):
+            (a @ b)
+        e1.record()
+        torch.cuda.synchronize()
+        best = max(best, 4 * 2 * 4096 ** 3 / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+    torch.backends.cuda.matmul.allow_tf32 = prev
+    return best
+
+
+def _oracle_worker(args):
+    """env-steps/s of the CPU oracle stack in this process: (n_envs, n_steps, seed) -> (steps, seconds)."""
+    n_envs, n_steps, seed = args
+    import random
+
+    import numpy as np
+
+    from drloco_b200.walkers import make_spec
+    from oracle.env_oracle import OracleVecEnv
+    from oracle.physics import OraclePhysics
+    spec = make_spec()
+    random.seed(seed)
+    np.random.seed(seed)
+    rng = np.random.default_rng(seed)
+    venv = OracleVecEnv(spec, n_envs, lambda: OraclePhysics(spec.model))
+    venv.reset()
+    for _ in range(5):
+        venv.step(rng.uniform(-1, 1, (n_envs, spec.act_dim)).astype(np.float32))
+    t0 = time.perf_counter()
+    for _ in range(n_steps):
+        venv.step(rng.uniform(-1, 1, (n_envs, spec.act_dim)).astype(np.float32))
+    return n_envs * n_steps, time.perf_counter() - t0
+
+
+def cpu_baseline_single(budget_s: float = 12.0):
+    """bounded single-core sample of the oracle stack (kind = "port")."""
+    from oracle import physics
+    physics.build()
+    steps, secs = _oracle_worker((8, 50, 0))
+    rate = steps / secs
+    n_steps = max(50, int(budget_s * rate / 8))
+    steps, secs = _oracle_worker((8, n_steps, 1))
+    return {"value": steps / secs, "unit": "env-steps/s", "cores": 1, "kind": "port",
+            "sample": f"8 envs x {n_steps} control steps, W3D RK4, random actions, numpy env logic + float64 C physics "
+                      f"(oracle/), {secs:.1f} s"}
+
+
+def run_reference(args):
+    """--impl reference: the reference path (SubprocVecEnv: one process per env) restated by the oracle on all cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    from oracle import physics
+    physics.build()
+    cores = os.cpu_count() or 1
+    per_proc_envs = 4
+    # size each step so that steps+warmup stay within a few minutes: one "step" = 40 control steps of all envs
+    ctrl_per_step = 40
+    ctx = mp.get_context("fork")
+    total_steps, t_total = 0, 0.0
+    with ctx.Pool(cores) as pool:
+        for k in range(args.warmup):
+            pool.map(_oracle_worker, [(per_proc_envs, 5, 100 + k * cores + c) for c in range(cores)])
+        t0 = time.perf_counter()
+        for k in range(args.steps):
+            res = pool.map(_oracle_worker, [(per_proc_envs, ctrl_per_step, k * cores + c) for c in range(cores)])
+            total_steps += sum(r[0] for r in res)
+        t_total = time.perf_counter() - t0
+    value = total_steps / t_total
+    sample = (f"{cores} processes x {per_proc_envs} envs x {ctrl_per_step} control steps per bench step; oracle stack "
+              "(reference env logic restated in numpy + float64 C restatement of the MuJoCo pipeline); MuJoCo itself "
+              "is not installable here")
+    line = {"impl": "reference", "metric": "env-steps/s incl. DeepMimic reward", "value": value, "unit": "env-steps/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": t_total / max(1, args.steps) * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic random actions on the shipped straight-walking mocap",
+            "config": {"workload": "MimicWalker3d straight walking, random-action step+reward throughput",
+                       "envs": cores * per_proc_envs, "integrator": "rk4"},
+            "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--envs-per-gpu", type=int, default=ENVS_PER_GPU)
+    ap.add_argument("--integrator", default="rk4", choices=["rk4", "euler"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from drloco_b200.config import EnvConfig
+    from drloco_b200.vec_env import B200MimicVecEnv, B200VecNormalize
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    n = args.envs_per_gpu
+    cfg = EnvConfig(env_id=ENV_ID, integrator=args.integrator)
+    env = B200MimicVecEnv(ENV_ID, num_envs=n, device=f"cuda:{local}", seed=rank, cfg=cfg, env_id_offset=rank * n)
+    vn = B200VecNormalize(env, distributed=world > 1)
+    dev = env.device
+    g = torch.Generator(device=dev)
+    g.manual_seed(1234 + rank)
+    ring = torch.rand(64, n, env.act_dim, device=dev, generator=g) * 2 - 1     # pre-generated action ring (§8d)
+    flush = torch.empty(192 * 1024 * 1024 // 4, device=dev)                    # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    vn.reset_tensor()
+    for k in range(args.warmup):
+        vn.step_tensor(ring[k % 64])
+    barrier()
+    env.reset_stats()
+
+    # ---- timed region 1: device-resident (value), with per-kernel timing of the fused step kernel ----
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = env.launches + vn.launches
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    ev[0].record()
+    for k in range(args.steps):
+        a = ring[k % 64]
+        kev[k][0].record()
+        obs, rew, done = env.step_tensor(a)
+        kev[k][1].record()
+        vn._normalize(obs, rew, done)
+    ev[1].record()
+    barrier()
+    clocks = sampler.stop()
+    ms_total = ev[0].elapsed_time(ev[1])
+    kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
+    launches = env.launches + vn.launches - launches0
+    t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    value = world * n * args.steps / (ms_total * 1e-3)
+    stats = env.stats()
+
+    # ---- timed region 2: end to end through the numpy API (host actions in, host obs/rew/done out) ----
+    e2e = None
+    if not args.no_e2e:
+        host_actions = [np.random.default_rng(rank * 1000 + k).uniform(-1, 1, (n, env.act_dim)).astype(np.float32)
+                        for k in range(8)]
+        k2 = max(10, args.steps // 4)
+        for k in range(3):
+            vn.step(host_actions[k % 8])
+        barrier()
+        flush.fill_(1.0)
+        barrier()
+        ev2 = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        ev2[0].record()
+        acc = 0.0
+        for k in range(k2):
+            o, r, d, infos = vn.step(host_actions[k % 8])
+            acc += float(r[0])
+        ev2[1].record()
+        barrier()
+        t2 = torch.tensor([ev2[0].elapsed_time(ev2[1])], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * n * k2 / (float(t2.item()) * 1e-3), "unit": "env-steps/s",
+               "h2d_bytes_per_step": n * env.act_dim * 4, "d2h_bytes_per_step": n * (env.obs_dim * 4 + 4 + 1),
+               "steps": k2}
+
+    if rank == 0:
+        peaks, which = _peaks()
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        achieved_gbs = ALGO_BYTES_PER_ENV_STEP * n / (kernel_ms * 1e-3) / 1e9
+        fp32_peak = fp32_peak_tflops(torch)
+        achieved_tf = ALGO_FLOP_PER_ENV_STEP * n / (kernel_ms * 1e-3) / 1e12
+        line = {
+            "metric": "env-steps/s incl. DeepMimic reward", "value": value, "unit": "env-steps/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic random actions U(-1,1) on the shipped straight-walking mocap, random-init (RSI) states",
+            "config": {"workload": "MimicWalker3d straight walking, %d batched envs per GPU, random-action step+reward "
+                                   "throughput (BASELINE.json configs[1])" % n,
+                       "envs_per_gpu": n, "integrator": args.integrator, "frame_skip": env.spec.frame_skip,
+                       "parallelism": f"env-sharded x{world}", "l2": "state re-read each step; 192 MB flush before e2e",
+                       "lanes_per_env": env.launch_info()["lanes_per_env"]},
+            "clocks": clocks,
+            "e2e": e2e,
+            "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": achieved_gbs / hbm_peak, "traffic": None, "peak_source": which,
+                         "kernel": "mimic_step_kernel", "kernel_ms": kernel_ms,
+                         "note": "latency/FP32-bound by construction: 425 algorithmic bytes per env-step"},
+            "fp32": {"achieved_tflops": achieved_tf, "peak_tflops": fp32_peak,
+                     "frac": achieved_tf / fp32_peak if fp32_peak else None,
+                     "peak_source": "fp32 (no TF32) cuBLAS sgemm 4096^3 measured in this run",
+                     "algo_flop_per_env_step": ALGO_FLOP_PER_ENV_STEP},
+            "episode_stats": {"episodes": stats["episodes"], "mean_ep_len": stats["ep_len_sum"] / max(1.0, stats["episodes"]),
+                              "reset_rate_per_env_step": stats["episodes"] / max(1.0, stats["env_steps"]),
+                              "solver_iters_per_eval": stats["solver_iters"] / max(1.0, stats["dyn_evals"])},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline_single()
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

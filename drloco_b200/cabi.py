@@ -14,8 +14,10 @@ MAX_DOF, MAX_BODY, MAX_ACT, MAX_SPHERE, MAX_BOX, MAX_SITE, MAX_OBS, MAX_PHASE_JO
 INTEGRATOR_RK4, INTEGRATOR_EULER = 0, 1
 CURSOR_STEPWISE, CURSOR_WRAP = 0, 1
 PHASE_FROM_CURSOR, PHASE_FROM_JOINTS = 0, 1
-EXTRA_NAMES = ("pos_rew", "vel_rew", "com_rew", "walked_distance", "mean_abs_torque", "des_vel", "phase", "z_offset")
-EXTRA_COUNT = 8
+EXTRA_NAMES = ("pos_rew", "vel_rew", "com_rew", "walked_distance", "mean_abs_torque", "des_vel", "phase", "z_offset",
+               "ep_len_smoothed", "ep_ret_smoothed", "mean_reward_smoothed", "mean_ep_pos_rew_smoothed",
+               "mean_ep_vel_rew_smoothed", "mean_ep_com_rew_smoothed", "moved_distance", "mean_abs_ep_torque_smoothed")
+EXTRA_COUNT = 16
 STAT_NAMES = ("episodes", "ep_len_sum", "ep_ret_sum", "ep_mean_rew_sum", "pos_rew_sum", "vel_rew_sum", "com_rew_sum",
               "rew_steps", "moved_distance_sum", "abs_torque_sum", "env_steps", "blowups", "falls", "timeouts",
               "solver_iters", "dyn_evals")

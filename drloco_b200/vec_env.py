@@ -1,0 +1,529 @@
+"""B200MimicVecEnv: N DeepMimic walker environments on one B200 behind the SB3 ``VecEnv`` surface.
+
+Replaces, as one unit, what reference ``drloco.common.utils.vec_env`` (utils.py:97-134) builds:
+``VecNormalize(SubprocVecEnv([Monitor(MimicWalker3dEnv())] * n))``.  The host side here is plumbing only — PyTorch owns
+device memory and streams, ctypes passes raw pointers to libdrloco_b200.so (include/drloco_b200.h); every environment
+step is one fused CUDA kernel launch (csrc/mimic_step.cu).  There is no CPU fallback.
+
+Two ways to step:
+  * SB3-compatible numpy API: ``reset() -> obs``, ``step_async(actions)``, ``step_wait() -> (obs, rews, dones, infos)``
+    with ``infos[i]["terminal_observation"]`` for finished episodes (host<->device copies every call);
+  * tensor API: ``step_tensor(actions_cuda) -> (obs, rew, done)`` — everything stays in HBM, nothing synchronises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Any, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import cabi, config as cfgm, lib
+from .walkers import WalkerSpec, make_spec
+
+
+class Box:
+    """Minimal stand-in for gym.spaces.Box (gym is optional at run time)."""
+
+    def __init__(self, low, high, shape=None, dtype=np.float32):
+        self.dtype = np.dtype(dtype)
+        self.low = np.broadcast_to(np.asarray(low, self.dtype), shape if shape is not None else np.shape(low)).copy()
+        self.high = np.broadcast_to(np.asarray(high, self.dtype), self.low.shape).copy()
+        self.shape = self.low.shape
+
+    def sample(self):
+        lo = np.where(np.isfinite(self.low), self.low, -1.0)
+        hi = np.where(np.isfinite(self.high), self.high, 1.0)
+        return np.random.uniform(lo, hi).astype(self.dtype)
+
+    def __repr__(self):
+        return f"Box({self.low.min()}, {self.high.max()}, {self.shape}, {self.dtype})"
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+class B200MimicVecEnv:
+    """Batched MimicEnv.  Same attribute / method names as SB3's VecEnv."""
+
+    metadata = {"render.modes": []}
+
+    def __init__(self, env_id: str = cfgm.STRAIGHT_WALKER, num_envs: int = 4096, device="cuda:0",
+                 seed: int = 33, cfg: Optional[cfgm.EnvConfig] = None, mocap_path: Optional[str] = None,
+                 env_id_offset: int = 0, lanes_per_env: int = 0, spec: Optional[WalkerSpec] = None):
+        self._lib = lib.load()                       # raises when the CUDA library is missing
+        if not torch.cuda.is_available():
+            raise lib.DrlError("drloco_b200 needs a CUDA device (there is no CPU path)")
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise lib.DrlError(f"device must be a CUDA device, got {device}")
+        self.cfg = cfg or (spec.cfg if spec is not None else cfgm.EnvConfig(env_id=env_id, seed=seed))
+        self.spec = spec or make_spec(self.cfg, mocap_path)
+        self.num_envs = int(num_envs)
+        self.obs_dim, self.act_dim = self.spec.obs_dim, self.spec.act_dim
+        m = self.spec.model
+        self.observation_space = Box(-np.inf, np.inf, (self.obs_dim,), np.float64)
+        self.action_space = Box(m.act_ctrlrange[:, 0], m.act_ctrlrange[:, 1], dtype=np.float32)   # mimic_env.py:256-262
+        self._handle = C.c_void_p()
+        c = self._make_config(seed, env_id_offset, lanes_per_env)
+        lib.check(self._lib.drl_create(C.byref(c), C.byref(self._handle)), "drl_create")
+        self._cm = cabi.pack_model(m)
+        lib.check(self._lib.drl_upload_model(self._handle, C.byref(self._cm)), "drl_upload_model")
+        self._upload_mocap()
+        with torch.cuda.device(self.device):
+            N, D = self.num_envs, self.obs_dim
+            dev = self.device
+            self.obs = torch.zeros(N, D, device=dev)
+            self.rew = torch.zeros(N, device=dev)
+            self.done = torch.zeros(N, dtype=torch.uint8, device=dev)
+            self.terminal_obs = torch.zeros(N, D, device=dev)
+            self._actions = torch.zeros(N, self.act_dim, device=dev)
+            self._extras = torch.zeros(N, cabi.EXTRA_COUNT, device=dev)
+            self._stats = torch.zeros(cabi.STATS_COUNT, dtype=torch.float64, device=dev)
+            # pinned staging for the numpy API
+            self._h_act = torch.zeros(N, self.act_dim).pin_memory()
+            self._h_obs = torch.zeros(N, D).pin_memory()
+            self._h_tobs = torch.zeros(N, D).pin_memory()
+            self._h_rew = torch.zeros(N).pin_memory()
+            self._h_done = torch.zeros(N, dtype=torch.uint8).pin_memory()
+        self._inj = None
+        self._pending = False
+        self._ep_lens_base = 0        # set_attr('ep_lens', []) marks the ring position (callback.py:69-70)
+        self._closed = False
+        self.launches = 0             # kernels launched through this env (bench: gpu_launches)
+
+    # ------------------------------------------------------------------ construction helpers
+    def _make_config(self, seed, env_id_offset, lanes_per_env) -> cabi.DrlConfig:
+        s, cfg = self.spec, self.cfg
+        c = cabi.DrlConfig()
+        c.num_envs = self.num_envs
+        c.device = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        c.frame_skip = s.frame_skip
+        c.integrator = {"rk4": cabi.INTEGRATOR_RK4, "euler": cabi.INTEGRATOR_EULER}[cfg.integrator]
+        c.ep_dur_max = cfg.ep_dur_max
+        c.mirror_policy = 1 if s.mirror else 0
+        c.phase_mode = cabi.PHASE_FROM_CURSOR if s.phase_from_cursor else cabi.PHASE_FROM_JOINTS
+        c.n_phase_joints = len(s.phase_joints)
+        for i, j in enumerate(s.phase_joints):
+            c.phase_joints[i] = j
+        c.eval_n_times = cfg.eval_n_times
+        c.ctrl_freq = float(cfg.ctrl_freq)
+        for i in range(4):
+            c.rew_weights[i] = cfg.rew_weights[i]
+        c.rew_scale, c.alive_bonus, c.fall_z = cfg.rew_scale, cfg.alive_bonus, cfg.fall_z
+        c.seed, c.env_id_offset = int(seed) & (2 ** 64 - 1), int(env_id_offset)
+        c.obs_dim, c.act_dim = s.obs_dim, s.act_dim
+        oi, osn, ai, asn = s.mirror_tables()
+        for i in range(s.obs_dim):
+            c.mirror_obs_idx[i], c.mirror_obs_sign[i] = int(oi[i]), float(osn[i])
+        for i in range(s.act_dim):
+            c.mirror_act_idx[i], c.mirror_act_sign[i] = int(ai[i]), float(asn[i])
+        c.lanes_per_env = lanes_per_env
+        return c
+
+    def _upload_mocap(self):
+        t = self.spec.mocap
+        arrs = dict(ref=np.ascontiguousarray(t.ref, np.float64), off=np.ascontiguousarray(t.step_off, np.int32),
+                    ln=np.ascontiguousarray(t.step_len, np.int32), left=np.ascontiguousarray(t.left_step, np.uint8),
+                    vel=np.ascontiguousarray(t.step_vel, np.float64),
+                    lastx=np.ascontiguousarray(t.step_last_comx, np.float64))
+        pre = None if t.des_vel_prefix is None else np.ascontiguousarray(t.des_vel_prefix, np.float64)
+        p = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)   # noqa: E731
+        lib.check(self._lib.drl_upload_mocap(self._handle, t.cursor_mode, t.increment, p(arrs["ref"]), t.n_samples,
+                                             p(arrs["off"]), p(arrs["ln"]), p(arrs["left"]), p(arrs["vel"]),
+                                             p(arrs["lastx"]), t.n_steps, t.com_z_col, p(pre), t.des_vel_window),
+                  "drl_upload_mocap")
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _inject_tensors(self, inject):
+        if inject is None:
+            return None, None
+        istep, pos = inject
+        dev = self.device
+        return (torch.as_tensor(np.asarray(istep, np.int32), device=dev), torch.as_tensor(np.asarray(pos, np.int32), device=dev))
+
+    # ------------------------------------------------------------------ tensor API (no host synchronisation)
+    def reset_tensor(self, mask: Optional[torch.Tensor] = None, inject=None) -> torch.Tensor:
+        ii, ip = self._inject_tensors(inject)
+        with torch.cuda.device(self.device):
+            lib.check(self._lib.drl_reset(self._handle, _ptr(mask), _ptr(ii), _ptr(ip), _ptr(self.obs), self._stream()),
+                      "drl_reset")
+        self.launches += 1
+        return self.obs
+
+    def step_tensor(self, actions: torch.Tensor, inject=None) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        """actions: float32 CUDA tensor [N, act_dim].  Returns (obs, rew, done) device tensors owned by the env and
+        overwritten by the next step; ``self.terminal_obs`` rows of done envs hold the pre-reset observation."""
+        if actions.dtype != torch.float32 or not actions.is_cuda or not actions.is_contiguous() \
+                or tuple(actions.shape) != (self.num_envs, self.act_dim):
+            raise ValueError("actions must be a contiguous float32 CUDA tensor of shape [num_envs, act_dim]")
+        ii, ip = self._inject_tensors(inject)
+        with torch.cuda.device(self.device):
+            lib.check(self._lib.drl_step(self._handle, _ptr(actions), _ptr(self.obs), _ptr(self.rew), _ptr(self.done),
+                                         _ptr(self.terminal_obs), _ptr(ii), _ptr(ip), self._stream()), "drl_step")
+        self.launches += 1
+        return self.obs, self.rew, self.done
+
+    # ------------------------------------------------------------------ SB3 VecEnv API (numpy)
+    def reset(self, inject=None) -> np.ndarray:
+        self.reset_tensor(None, inject)
+        self._h_obs.copy_(self.obs, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return self._h_obs.numpy().astype(np.float64)
+
+    def step_async(self, actions, inject=None) -> None:
+        a = np.ascontiguousarray(actions, np.float32).reshape(self.num_envs, self.act_dim)
+        self._h_act.numpy()[...] = a
+        self._actions.copy_(self._h_act, non_blocking=True)
+        self.step_tensor(self._actions, inject)
+        self._h_obs.copy_(self.obs, non_blocking=True)
+        self._h_rew.copy_(self.rew, non_blocking=True)
+        self._h_done.copy_(self.done, non_blocking=True)
+        self._h_tobs.copy_(self.terminal_obs, non_blocking=True)
+        self._pending = True
+
+    def step_wait(self):
+        if not self._pending:
+            raise RuntimeError("step_wait() without step_async()")
+        torch.cuda.current_stream(self.device).synchronize()
+        self._pending = False
+        obs = self._h_obs.numpy().astype(np.float64)
+        rew = self._h_rew.numpy().astype(np.float64)
+        done = self._h_done.numpy().astype(bool)
+        infos: List[dict] = [{} for _ in range(self.num_envs)]
+        if done.any():
+            tobs = self._h_tobs.numpy()
+            for i in np.nonzero(done)[0]:
+                infos[i]["terminal_observation"] = tobs[i].astype(np.float64)
+        return obs, rew, done, infos
+
+    def step(self, actions, inject=None):
+        self.step_async(actions, inject)
+        return self.step_wait()
+
+    def close(self) -> None:
+        if not self._closed and self._handle:
+            self._lib.drl_destroy(self._handle)
+            self._handle = C.c_void_p()
+            self._closed = True
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def seed(self, seed: Optional[int] = None):
+        """The RSI stream is keyed at construction (counter-based generator); kept for interface compatibility."""
+        return [None if seed is None else seed + i for i in range(self.num_envs)]
+
+    def env_is_wrapped(self, wrapper_class, indices=None):
+        return [False] * len(self._indices(indices))
+
+    def get_images(self):
+        raise NotImplementedError("rendering is out of scope (SURVEY.md §2 #15)")
+
+    def _indices(self, indices) -> List[int]:
+        if indices is None:
+            return list(range(self.num_envs))
+        if isinstance(indices, int):
+            return [indices]
+        return list(indices)
+
+    # ---- attributes the reference's callback reads through get_attr (callback.py:106-108,142,162-164,227) ----
+    def extras(self) -> torch.Tensor:
+        with torch.cuda.device(self.device):
+            lib.check(self._lib.drl_get_extras(self._handle, _ptr(self._extras), self._stream()), "drl_get_extras")
+        self.launches += 1
+        return self._extras
+
+    def stats(self) -> dict:
+        with torch.cuda.device(self.device):
+            lib.check(self._lib.drl_get_stats(self._handle, _ptr(self._stats), self._stream()), "drl_get_stats")
+        return dict(zip(cabi.STAT_NAMES, self._stats.cpu().tolist()))
+
+    def stats_tensor(self) -> torch.Tensor:
+        """packed float64 sums (all-reduce payload for multi-GPU episode statistics)."""
+        with torch.cuda.device(self.device):
+            lib.check(self._lib.drl_get_stats(self._handle, _ptr(self._stats), self._stream()), "drl_get_stats")
+        return self._stats
+
+    def reset_stats(self):
+        lib.check(self._lib.drl_reset_stats(self._handle, self._stream()), "drl_reset_stats")
+
+    def episode_lengths(self) -> np.ndarray:
+        cap = 1 << 16
+        with torch.cuda.device(self.device):
+            ln = torch.zeros(cap, dtype=torch.int32, device=self.device)
+            total = C.c_int64()
+            lib.check(self._lib.drl_get_episode_ring(self._handle, _ptr(ln), None, cap, C.byref(total), self._stream()),
+                      "drl_get_episode_ring")
+        total = total.value
+        n_new = min(total - self._ep_lens_base, cap)
+        if n_new <= 0:
+            return np.zeros(0, np.int32)
+        host = ln.cpu().numpy()
+        idx = (np.arange(total - n_new, total) % cap)
+        return host[idx]
+
+    def get_attr(self, attr_name: str, indices=None) -> List[Any]:
+        idx = self._indices(indices)
+        if attr_name in cabi.EXTRA_NAMES:
+            col = cabi.EXTRA_NAMES.index(attr_name)
+            vals = self.extras()[:, col].cpu().numpy()
+            return [float(vals[i]) for i in idx]
+        if attr_name == "ep_lens":
+            # the reference returns one list per env and the callback flattens them (callback.py:227-230)
+            lens = self.episode_lengths().tolist()
+            return [lens] + [[] for _ in idx[1:]]
+        if attr_name in ("num_envs", "obs_dim", "act_dim"):
+            return [getattr(self, attr_name)] * len(idx)
+        if attr_name in ("ep_dur", "i_step", "pos"):
+            cur = self.get_state()[2]
+            col = {"i_step": 0, "pos": 1, "ep_dur": 3}[attr_name]
+            return [int(cur[i, col]) for i in idx]
+        raise AttributeError(f"B200MimicVecEnv has no per-env attribute {attr_name!r}")
+
+    def set_attr(self, attr_name: str, value: Any, indices=None) -> None:
+        if attr_name == "ep_lens":               # callback.py:69-70 empties the list roughly every 1M steps
+            total = C.c_int64()
+            lib.check(self._lib.drl_get_episode_ring(self._handle, None, None, 0, C.byref(total), self._stream()),
+                      "drl_get_episode_ring")
+            self._ep_lens_base = total.value
+            return
+        raise AttributeError(f"cannot set per-env attribute {attr_name!r}")
+
+    def env_method(self, method_name: str, *args, indices=None, **kwargs) -> List[Any]:
+        idx = self._indices(indices)
+        if method_name == "activate_evaluation":             # mimic_env.py:245
+            lib.check(self._lib.drl_set_eval_mode(self._handle, 1), "drl_set_eval_mode")
+            return [None] * len(idx)
+        if method_name == "get_walked_distance":              # mimic_env.py:295
+            return self.get_attr("walked_distance", indices)
+        if method_name == "get_COM_Z_position":               # mimic_env.py:128
+            q = self.get_state()[0]
+            return [float(q[i, 2]) for i in idx]
+        raise AttributeError(f"env_method {method_name!r} is not served by the batched env")
+
+    # ------------------------------------------------------------------ state access (parity tests)
+    def get_state(self):
+        N = self.num_envs
+        with torch.cuda.device(self.device):
+            q = torch.zeros(N, self.spec.model.nv, device=self.device)
+            v = torch.zeros_like(q)
+            cur = torch.zeros(N, 4, dtype=torch.int32, device=self.device)
+            lib.check(self._lib.drl_get_state(self._handle, _ptr(q), _ptr(v), _ptr(cur), self._stream()), "drl_get_state")
+        self.launches += 1
+        return q.cpu().numpy(), v.cpu().numpy(), cur.cpu().numpy()
+
+    def set_state(self, qpos=None, qvel=None, cursor=None):
+        dev = self.device
+        q = None if qpos is None else torch.as_tensor(np.ascontiguousarray(qpos, np.float32), device=dev)
+        v = None if qvel is None else torch.as_tensor(np.ascontiguousarray(qvel, np.float32), device=dev)
+        c = None if cursor is None else torch.as_tensor(np.ascontiguousarray(cursor, np.int32), device=dev)
+        with torch.cuda.device(dev):
+            lib.check(self._lib.drl_set_state(self._handle, _ptr(q), _ptr(v), _ptr(c), self._stream()), "drl_set_state")
+            torch.cuda.current_stream(dev).synchronize()
+        self.launches += 1
+
+    def launch_info(self) -> dict:
+        vals = [C.c_int32() for _ in range(4)]
+        lib.check(self._lib.drl_launch_info(self._handle, *[C.byref(v) for v in vals]), "drl_launch_info")
+        return dict(zip(("lanes_per_env", "block_threads", "grid_blocks", "smem_bytes"), [v.value for v in vals]))
+
+    def debug_set(self, frame_skip_override=-1, block_threads=0, enable_dump=False):
+        lib.check(self._lib.drl_debug_set(self._handle, frame_skip_override, block_threads, int(enable_dump)),
+                  "drl_debug_set")
+
+    def debug_read(self) -> np.ndarray:
+        out = np.zeros((self.num_envs, 40, 32), np.float32)
+        lib.check(self._lib.drl_debug_read(self._handle, out.ctypes.data_as(C.c_void_p), out.size), "drl_debug_read")
+        return out
+
+
+class RunningMeanStdView:
+    """Read-only view with SB3's RunningMeanStd attribute names (mean, var, count)."""
+
+    def __init__(self, mean, var, count):
+        self.mean, self.var, self.count = mean, var, count
+
+
+class B200VecNormalize:
+    """SB3 VecNormalize semantics on the device (utils.py:130-132: norm_obs=True, norm_reward=norm_rew, clip 10/10,
+    gamma=0.99, epsilon=1e-8).  With ``torch.distributed`` initialised, the packed batch moments are all-reduced
+    (NCCL) so that every rank holds identical running statistics."""
+
+    def __init__(self, venv: B200MimicVecEnv, training=True, norm_obs=True, norm_reward=True, clip_obs=10.0,
+                 clip_reward=10.0, gamma=0.99, epsilon=1e-8, distributed: Optional[bool] = None,
+                 stats_sync_every: int = 1):
+        self.venv = venv
+        self.num_envs, self.device = venv.num_envs, venv.device
+        self.observation_space, self.action_space = venv.observation_space, venv.action_space
+        self.training, self.norm_obs, self.norm_reward = training, norm_obs, norm_reward
+        self.clip_obs, self.clip_reward, self.gamma, self.epsilon = clip_obs, clip_reward, gamma, epsilon
+        D = venv.obs_dim
+        self._D = D
+        dev = self.device
+        rms = torch.zeros(2 * D + 4, dtype=torch.float64, device=dev)
+        rms[D:2 * D] = 1.0
+        rms[2 * D] = 1e-4                      # RunningMeanStd(epsilon=1e-4)
+        rms[2 * D + 2] = 1.0
+        rms[2 * D + 3] = 1e-4
+        self._rms = [rms, rms.clone()]
+        self._cur = 0
+        self._packed = torch.zeros(2 * D + 3, dtype=torch.float64, device=dev)
+        self.ret = torch.zeros(self.num_envs, device=dev)
+        self.norm_obs_buf = torch.zeros(self.num_envs, D, device=dev)
+        self.norm_rew_buf = torch.zeros(self.num_envs, device=dev)
+        if distributed is None:
+            distributed = torch.distributed.is_available() and torch.distributed.is_initialized() \
+                and torch.distributed.get_world_size() > 1
+        self.distributed = distributed
+        self.stats_sync_every = max(1, int(stats_sync_every))
+        self._since_sync = 0
+        self._lib = venv._lib
+        self.launches = 0
+
+    # -- SB3 attribute surface ----------------------------------------------------------------------
+    @property
+    def obs_rms(self):
+        r, D = self._rms[self._cur], self._D
+        return RunningMeanStdView(r[:D].cpu().numpy(), r[D:2 * D].cpu().numpy(), float(r[2 * D]))
+
+    @property
+    def ret_rms(self):
+        r, D = self._rms[self._cur], self._D
+        return RunningMeanStdView(float(r[2 * D + 1]), float(r[2 * D + 2]), float(r[2 * D + 3]))
+
+    def _flags(self):
+        return (1 if self.training else 0) | (2 if self.norm_obs else 0) | (4 if self.norm_reward else 0)
+
+    def _normalize(self, obs, rew, done):
+        v = self.venv
+        st = v._stream()
+        with torch.cuda.device(self.device):
+            packed = None
+            if self.training:
+                lib.check(self._lib.drl_vecnorm_moments(_ptr(obs), self.num_envs, self._D, _ptr(rew),
+                                                        _ptr(self.ret) if rew is not None else None,
+                                                        float(self.gamma), _ptr(self._packed), st), "drl_vecnorm_moments")
+                self.launches += 1
+                if self.distributed:
+                    torch.distributed.all_reduce(self._packed, op=torch.distributed.ReduceOp.SUM)
+                packed = self._packed
+            src, dst = self._rms[self._cur], self._rms[1 - self._cur]
+            lib.check(self._lib.drl_vecnorm_apply(_ptr(obs), _ptr(self.norm_obs_buf), _ptr(rew),
+                                                  _ptr(self.norm_rew_buf) if rew is not None else None,
+                                                  self.num_envs, self._D, _ptr(packed), _ptr(src), _ptr(dst),
+                                                  _ptr(self.ret), _ptr(done), float(self.clip_obs),
+                                                  float(self.clip_reward), float(self.epsilon), self._flags(), st),
+                      "drl_vecnorm_apply")
+            self.launches += 1
+            self._cur = 1 - self._cur
+
+    # -- tensor API -----------------------------------------------------------------------------------
+    def reset_tensor(self, inject=None):
+        obs = self.venv.reset_tensor(None, inject)
+        self.ret.zero_()
+        self._normalize(obs, None, None)
+        return self.norm_obs_buf
+
+    def step_tensor(self, actions, inject=None):
+        obs, rew, done = self.venv.step_tensor(actions, inject)
+        self._normalize(obs, rew, done)
+        return self.norm_obs_buf, self.norm_rew_buf, done
+
+    # -- SB3 numpy API -----------------------------------------------------------------------------------
+    def reset(self, inject=None):
+        return self.reset_tensor(inject).cpu().numpy()
+
+    def step_async(self, actions, inject=None):
+        a = torch.as_tensor(np.ascontiguousarray(actions, np.float32), device=self.device)
+        self._out = self.step_tensor(a, inject)
+
+    def step_wait(self):
+        obs, rew, done = self._out
+        done_h = done.cpu().numpy().astype(bool)
+        infos = [{} for _ in range(self.num_envs)]
+        if done_h.any():
+            tobs = self.normalize_obs(self.venv.terminal_obs).cpu().numpy()
+            for i in np.nonzero(done_h)[0]:
+                infos[i]["terminal_observation"] = tobs[i]
+        return obs.cpu().numpy(), rew.cpu().numpy(), done_h, infos
+
+    def step(self, actions, inject=None):
+        self.step_async(actions, inject)
+        return self.step_wait()
+
+    def normalize_obs(self, obs: torch.Tensor) -> torch.Tensor:
+        if not self.norm_obs:
+            return obs
+        r, D = self._rms[self._cur], self._D
+        mean, var = r[:D].float(), r[D:2 * D]
+        return torch.clamp((obs - mean) / torch.sqrt(var + self.epsilon).float(), -self.clip_obs, self.clip_obs)
+
+    def get_original_obs(self):
+        return self.venv.obs
+
+    def get_original_reward(self):
+        return self.venv.rew
+
+    # -- save / load: same payload as the reference's pickled VecNormalize statistics (utils.py:183-184, 234-240) -----
+    def state_dict(self) -> dict:
+        r, D = self._rms[self._cur].cpu().numpy(), self._D
+        return dict(obs_mean=r[:D].copy(), obs_var=r[D:2 * D].copy(), obs_count=float(r[2 * D]),
+                    ret_mean=float(r[2 * D + 1]), ret_var=float(r[2 * D + 2]), ret_count=float(r[2 * D + 3]),
+                    clip_obs=self.clip_obs, clip_reward=self.clip_reward, gamma=self.gamma, epsilon=self.epsilon,
+                    norm_obs=self.norm_obs, norm_reward=self.norm_reward)
+
+    def load_state_dict(self, sd: dict) -> None:
+        D = self._D
+        r = np.zeros(2 * D + 4)
+        r[:D], r[D:2 * D], r[2 * D] = sd["obs_mean"], sd["obs_var"], sd["obs_count"]
+        r[2 * D + 1], r[2 * D + 2], r[2 * D + 3] = sd["ret_mean"], sd["ret_var"], sd["ret_count"]
+        self._rms[self._cur].copy_(torch.as_tensor(r, device=self.device))
+        for k in ("clip_obs", "clip_reward", "gamma", "epsilon", "norm_obs", "norm_reward"):
+            setattr(self, k, sd[k])
+
+    def save(self, path: str) -> None:
+        import pickle
+        with open(path, "wb") as f:
+            pickle.dump(self.state_dict(), f)
+
+    @staticmethod
+    def load(path: str, venv: B200MimicVecEnv) -> "B200VecNormalize":
+        import pickle
+        with open(path, "rb") as f:
+            sd = pickle.load(f)
+        vn = B200VecNormalize(venv)
+        vn.load_state_dict(sd)
+        return vn
+
+    # -- pass-through ----------------------------------------------------------------------------------------
+    def get_attr(self, name, indices=None):
+        return self.venv.get_attr(name, indices)
+
+    def set_attr(self, name, value, indices=None):
+        return self.venv.set_attr(name, value, indices)
+
+    def env_method(self, name, *a, indices=None, **k):
+        return self.venv.env_method(name, *a, indices=indices, **k)
+
+    def seed(self, seed=None):
+        return self.venv.seed(seed)
+
+    def close(self):
+        self.venv.close()
+
+
+def vec_env(env_id: str, num_envs: int = 4, seed: int = 33, norm_rew: bool = True, load_path: Optional[str] = None,
+            device="cuda:0", **kw) -> B200VecNormalize:
+    """Drop-in for reference ``drloco.common.utils.vec_env`` (utils.py:97-134): same arguments, returns the normalised
+    vectorised environment (here: B200VecNormalize(B200MimicVecEnv))."""
+    venv = B200MimicVecEnv(env_id, num_envs=num_envs, device=device, seed=seed, **kw)
+    if load_path is not None:
+        return B200VecNormalize.load(load_path, venv)
+    return B200VecNormalize(venv, norm_obs=True, norm_reward=norm_rew)

@@ -164,7 +164,11 @@ typedef enum {
   DRL_EXTRA_WALKED_DISTANCE = 3,                                         /* mimic_env.py:295 */
   DRL_EXTRA_MEAN_ABS_TORQUE = 4,                                         /* mimic_env.py:251-253 */
   DRL_EXTRA_DES_VEL = 5, DRL_EXTRA_PHASE = 6, DRL_EXTRA_Z_OFFSET = 7,
-  DRL_EXTRA_COUNT = 8
+  /* Monitor attributes, per env (monitor_wrapper.py:104-133), exponentially smoothed at every episode end */
+  DRL_EXTRA_EP_LEN_SMOOTHED = 8, DRL_EXTRA_EP_RET_SMOOTHED = 9, DRL_EXTRA_MEAN_REWARD_SMOOTHED = 10,
+  DRL_EXTRA_MEAN_EP_POS_REW_SMOOTHED = 11, DRL_EXTRA_MEAN_EP_VEL_REW_SMOOTHED = 12,
+  DRL_EXTRA_MEAN_EP_COM_REW_SMOOTHED = 13, DRL_EXTRA_MOVED_DISTANCE = 14, DRL_EXTRA_MEAN_ABS_EP_TORQUE_SMOOTHED = 15,
+  DRL_EXTRA_COUNT = 16
 } DrlExtra;
 int drl_get_extras(DrlEnv* env, float* extras, void* stream);
 
@@ -189,6 +193,25 @@ int drl_get_episode_ring(DrlEnv* env, int32_t* ep_len, float* ep_ret, int32_t ca
 
 /* MimicEnv.activate_evaluation (mimic_env.py:245): deterministic init states (straight_walk_trajecs.py:237-265) */
 int drl_set_eval_mode(DrlEnv* env, int32_t on);
+
+/* test / tuning hooks: frame_skip_override >= 0 replaces cfg.frame_skip (0 = environment logic only, used to test the
+ * reward / cursor / reset path on injected states); block_threads > 0 sets the CTA size; enable_dump keeps, per env, the
+ * intermediate results of the last dynamics evaluation (mass matrix, bias force, qacc) for drl_debug_read (host buffer). */
+int drl_debug_set(DrlEnv* env, int32_t frame_skip_override, int32_t block_threads, int32_t enable_dump);
+int drl_debug_read(DrlEnv* env, float* host_out, int32_t n_floats);
+
+/* VecNormalize on the device — replaces SB3 VecNormalize.step_wait / reset around the env (utils.py:130-132).
+ * moments: ret = ret*gamma + rew (in place; skipped when rew == NULL) and
+ *          packed[2d+3] = { sum_obs[d], sumsq_obs[d], n, sum_ret, sumsq_ret } in float64 — the all-reduce(sum) payload.
+ * apply  : merges `packed` into the running statistics rms = { mean[d], var[d], count, ret_mean, ret_var, ret_count }
+ *          (RunningMeanStd.update_from_moments; rms_in -> rms_out, must not alias), then writes
+ *          obs_out = clip((obs_in-mean)/sqrt(var+eps), +-clip_obs), rew_out = clip(rew_in/sqrt(ret_var+eps), +-clip_rew),
+ *          ret[done] = 0.  flags: bit0 training (update statistics), bit1 norm_obs, bit2 norm_reward. */
+int drl_vecnorm_moments(const float* obs, int32_t n, int32_t d, const float* rew, float* ret, float gamma,
+                        double* packed, void* stream);
+int drl_vecnorm_apply(const float* obs_in, float* obs_out, const float* rew_in, float* rew_out, int32_t n, int32_t d,
+                      const double* packed, const double* rms_in, double* rms_out, float* ret, const uint8_t* done,
+                      float clip_obs, float clip_rew, float eps, int32_t flags, void* stream);
 
 /* introspection for benchmarks */
 int drl_launch_info(DrlEnv* env, int32_t* lanes_per_env, int32_t* block_threads, int32_t* grid_blocks,

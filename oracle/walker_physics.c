@@ -266,6 +266,11 @@ static double impedance(const double* solimp, double pos) {
   return d0 + y * (dm - d0);
 }
 
+int g_solver_mode = 0, g_as_maxit = 50;
+long g_as_hist[64], g_as_fail = 0;
+void orc_set_solver(int mode, int maxit) { g_solver_mode = mode; g_as_maxit = maxit; memset(g_as_hist, 0, sizeof g_as_hist); g_as_fail = 0; }
+void orc_get_solver_stats(long* hist, long* fail) { memcpy(hist, g_as_hist, sizeof g_as_hist); *fail = g_as_fail; }
+
 typedef struct { double a; int i; } Brk;
 static int brk_cmp(const void* x, const void* y) {
   double a = ((const Brk*)x)->a, b = ((const Brk*)y)->a;
@@ -390,6 +395,40 @@ int orc_forward(const DrlWalkerModel* m, const double* q, const double* v, const
   double res[MAXROW];
   if (nrow == 0) {
     memcpy(a, a0, sizeof(double) * nv);
+  } else if (g_solver_mode == 1) {
+    /* experimental mirror of the GPU kernel's solver: primal active-set iteration with full Newton steps
+       (no line search); the fixed point is the same unique minimiser.  Statistics in g_as_hist. */
+    unsigned char act[MAXROW], nact[MAXROW];
+    for (int i = 0; i < nrow; i++) {
+      double s = -aref[i];
+      for (int j = 0; j < nv; j++) s += J[i][j] * a[j];
+      act[i] = s < 0;
+    }
+    int conv = 0;
+    for (iters = 0; iters < g_as_maxit; iters++) {
+      double H[NV * NV], rhs[NV];
+      memcpy(H, M, sizeof(double) * nv * nv);
+      memcpy(rhs, tau, sizeof(double) * nv);
+      for (int i = 0; i < nrow; i++)
+        if (act[i])
+          for (int r = 0; r < nv; r++) {
+            rhs[r] += D[i] * aref[i] * J[i][r];
+            for (int cc = 0; cc < nv; cc++) H[r * nv + cc] += D[i] * J[i][r] * J[i][cc];
+          }
+      if (chol_solve(H, rhs, nv)) return -1;
+      memcpy(a, rhs, sizeof(double) * nv);
+      int same = 1;
+      for (int i = 0; i < nrow; i++) {
+        double s = -aref[i];
+        for (int j = 0; j < nv; j++) s += J[i][j] * a[j];
+        nact[i] = s < 0;
+        if (nact[i] != act[i]) same = 0;
+      }
+      memcpy(act, nact, nrow);
+      if (same) { conv = 1; iters++; break; }
+    }
+    g_as_hist[iters < 63 ? iters : 63]++;
+    if (!conv) g_as_fail++;
   } else {
     for (iters = 0; iters < 200; iters++) {
       double g[NV], H[NV * NV], dlt[NV];

@@ -14,7 +14,8 @@
 
 namespace drl {
 size_t step_smem_bytes(int G, int envs_per_block);
-cudaError_t launch_step(const StepArgs& a, int nv, int G, int reset_only, int block, bool debug, cudaStream_t st);
+cudaError_t launch_step(const StepArgs& a, int nv, int G, int rk4, int reset_only, int block, bool debug,
+                        cudaStream_t st);
 cudaError_t launch_extras(const float* state_f, const float* last, float* out, int n, int G, cudaStream_t st);
 cudaError_t launch_state_copy(float* state_f, int* state_i, float* qpos, float* qvel, int* cursor, int n, int nv, int G,
                               int to_state, cudaStream_t st);
@@ -42,7 +43,7 @@ struct DrlEnv {
   DrlConfig cfg;
   DevModel hm;                 // host copy
   bool have_model = false, have_mocap = false;
-  int G = 16, block = 64, nv = 0;
+  int G = 16, block = 128, nv = 0;
   DevModel* d_model = nullptr;
   float* state_f = nullptr;
   int* state_i = nullptr;
@@ -145,8 +146,8 @@ extern "C" int drl_upload_model(DrlEnv* e, const DrlWalkerModel* m) {
     d.level_body[lv][d.level_count[lv]++] = b;
   }
   int G = m->nv <= 16 ? 16 : 32;
-  if (c.lanes_per_env == 32) G = 32;
-  else if (c.lanes_per_env != 0 && c.lanes_per_env != G) return fail(DRL_ERR_INVALID, "config: lanes_per_env must be 0, %d or 32", G);
+  if (c.lanes_per_env != 0 && c.lanes_per_env != G)
+    return fail(DRL_ERR_INVALID, "config: lanes_per_env must be 0 or %d for this model", G);
   for (int lv = 0; lv < d.nlevel; lv++)
     if (d.level_count[lv] * 3 > G) return fail(DRL_ERR_UNSUPPORTED, "model: too many bodies on one tree level");
   for (int b = 0; b < m->nb; b++)
@@ -274,7 +275,7 @@ extern "C" int drl_upload_model(DrlEnv* e, const DrlWalkerModel* m) {
   d.seed = c.seed; d.env_id_offset = c.env_id_offset;
   e->nv = m->nv;
   e->G = G;
-  e->block = 64;
+  e->block = 128;
   CUDA_TRY(cudaSetDevice(c.device));
   const size_t N = (size_t)c.num_envs;
   if (!e->d_model) {
@@ -385,7 +386,7 @@ extern "C" int drl_reset(DrlEnv* e, const uint8_t* mask, const int32_t* inj_iste
   StepArgs a = make_args(e);
   a.reset_mask = mask; a.inj_istep = inj_istep; a.inj_pos = inj_pos; a.obs = obs;
   a.debug = nullptr;
-  CUDA_TRY(launch_step(a, e->nv, e->G, 1, e->block, false, (cudaStream_t)stream));
+  CUDA_TRY(launch_step(a, e->nv, e->G, e->cfg.integrator == DRL_INTEGRATOR_RK4, 1, e->block, false, (cudaStream_t)stream));
   return DRL_OK;
 }
 
@@ -397,7 +398,9 @@ extern "C" int drl_step(DrlEnv* e, const float* actions, float* obs, float* rew,
   StepArgs a = make_args(e);
   a.actions = actions; a.obs = obs; a.rew = rew; a.done = done; a.terminal_obs = terminal_obs;
   a.inj_istep = inj_istep; a.inj_pos = inj_pos;
-  CUDA_TRY(launch_step(a, e->nv, e->G, 0, e->block, e->debug != nullptr, (cudaStream_t)stream));
+    const bool rk4 = e->cfg.integrator == DRL_INTEGRATOR_RK4;
+  if (e->debug && rk4) return fail(DRL_ERR_UNSUPPORTED, "drl_step: the dump variant exists for the Euler integrator only");
+  CUDA_TRY(launch_step(a, e->nv, e->G, rk4, 0, e->block, e->debug != nullptr, (cudaStream_t)stream));
   return DRL_OK;
 }
 

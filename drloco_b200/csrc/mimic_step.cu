@@ -9,17 +9,19 @@
 //   Monitor.step statistics                                              monitor_wrapper.py:88-166
 //   DummyVecEnv/SubprocVecEnv auto-reset with terminal_observation       (SB3 1.0)
 //
-// Mapping: one environment per group of G lanes (G = 16 for nv <= 16, 32 otherwise), lane j owns dof j:
-// its q/v/RK4 accumulators, its motion vector S_j and column j of the constraint Hessian live in registers for the
-// whole launch; per-env tree quantities (body frames, spatial inertias, velocities, contact Hessians) live in shared
-// memory; all frame_skip x 4 dynamics evaluations run inside the launch, HBM is touched once on entry and once on exit.
+// Mapping: one environment per group of G lanes (G = 16 for nv <= 16: two environments per warp; G = 32 otherwise),
+// lane j owns dof j: its q/v/RK4 accumulators, its motion vector S_j and column j of the constraint Hessian live in
+// registers for the whole launch; per-env tree quantities (body frames, spatial inertias, velocities, contact
+// Hessians) live in shared memory; all frame_skip x 4 dynamics evaluations run inside the launch, HBM is touched once
+// on entry and once on exit.  Control flow is kept warp-uniform (the two environments of a warp run in lockstep, with
+// predicated effects), so every shuffle / ballot / barrier uses the full-warp mask and compiles to a bare instruction.
 // Spatial quantities are expressed in world orientation about O = the root body origin (keeps fp32 cancellation
 // independent of how far the walker has travelled).
 //
 // Constraint solve per evaluation (same minimiser as MuJoCo's Newton solver, see oracle/walker_physics.c):
 //   H = M + sum_b S_b^T W_b S_b + diag(limits),   H qacc = tau - c + sum_b S_b^T u_b + limits
 // with W_b the 6x6 wrench-space Hessian of the active pyramid rows of all contacts on body b; primal active-set
-// iteration with full Newton steps, warm-started from the previous evaluation; Cholesky in registers via shuffles.
+// iteration with full Newton steps, warm-started from the previous evaluation; LDL^T in registers via shuffles.
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
@@ -32,6 +34,7 @@ namespace drl {
 constexpr int kNPass = 2;          // contact candidates per lane
 constexpr int kMaxSolverIter = 10;
 constexpr float kMinVal = 1e-15f;
+constexpr unsigned kFull = 0xFFFFFFFFu;
 
 template <int G>
 struct EnvSmem {
@@ -88,18 +91,22 @@ __device__ __forceinline__ Vec6 inertia_mul(const float* I, const Vec6& t) {
   float2 c = *reinterpret_cast<const float2*>(I + 8);   // Iyz Izz
   float m = a.x, hx = a.y, hy = a.z, hz = a.w;
   Vec6 r;
-  // angular: I w + h x v
   float cx, cy, cz;
-  cross3(cx, cy, cz, hx, hy, hz, t.v0, t.v1, t.v2);
+  cross3(cx, cy, cz, hx, hy, hz, t.v0, t.v1, t.v2);      // angular: I w + h x v
   r.w0 = b.x * t.w0 + b.y * t.w1 + b.z * t.w2 + cx;
   r.w1 = b.y * t.w0 + b.w * t.w1 + c.x * t.w2 + cy;
   r.w2 = b.z * t.w0 + c.x * t.w1 + c.y * t.w2 + cz;
-  // linear: m v + w x h
-  cross3(cx, cy, cz, t.w0, t.w1, t.w2, hx, hy, hz);
+  cross3(cx, cy, cz, t.w0, t.w1, t.w2, hx, hy, hz);      // linear: m v + w x h
   r.v0 = m * t.v0 + cx;
   r.v1 = m * t.v1 + cy;
   r.v2 = m * t.v2 + cz;
   return r;
+}
+
+// general solimp power (MuJoCo default is 2, handled inline by impedance())
+__device__ __noinline__ float impedance_pow(float x, float mid, float power) {
+  return (x <= mid) ? powf(x, power) / powf(mid, power - 1.f)
+                    : 1.f - powf(1.f - x, power) / powf(1.f - mid, power - 1.f);
 }
 
 __device__ __forceinline__ float impedance(const DevModel& M, float dist) {
@@ -112,8 +119,7 @@ __device__ __forceinline__ float impedance(const DevModel& M, float dist) {
   } else if (M.imp_power == 1.f) {
     y = x;
   } else {
-    y = (x <= M.imp_mid) ? powf(x, M.imp_power) / powf(M.imp_mid, M.imp_power - 1.f)
-                         : 1.f - powf(1.f - x, M.imp_power) / powf(1.f - M.imp_mid, M.imp_power - 1.f);
+    y = impedance_pow(x, M.imp_mid, M.imp_power);
   }
   return M.imp_d0 + y * (M.imp_dmax - M.imp_d0);
 }
@@ -121,15 +127,22 @@ __device__ __forceinline__ float impedance(const DevModel& M, float dist) {
 // per-lane role constants
 struct LaneConst {
   int l;               // lane within the env group
-  unsigned gmask;      // warp mask of the group
+  unsigned emask;      // lanes of this lane's environment within the warp
   bool isdof, isbody;
   int body, type, limited, last;
   float sign, ref, damping, armature, lo, hi, invw;
-  unsigned anc, desc, subb, supp_self;   // supp_self: body_supp of this lane's body role
+  unsigned anc, desc, subb;
 };
 
 struct Counters {
   int evals, iters;
+};
+
+// active set carried from one dynamics evaluation to the next (lane <-> contact candidate is a fixed mapping)
+struct ActiveSet {
+  unsigned bits[kNPass];  // active pyramid rows of this lane's candidate in each pass
+  unsigned prev_act;      // which of this lane's candidates were in contact at the previous evaluation
+  bool lbit, prev_lim;    // joint-limit row of this lane's dof
 };
 
 // symmetric 6x6 index into 21 packed entries (i <= j)
@@ -137,32 +150,34 @@ __device__ __forceinline__ constexpr int sym6(int i, int j) {
   return (i <= j) ? (i * 6 - (i * (i - 1)) / 2 + (j - i)) : (j * 6 - (j * (j - 1)) / 2 + (i - j));
 }
 
-// Cholesky solve with the matrix spread one column per lane: H[0..NV-1] rows of the column, H[NV] the rhs entry.
-// On exit returns x for this lane's row.  All lanes of the group must call.
+// does predicate p hold on any lane of this lane's environment?
+__device__ __forceinline__ bool env_any(bool p, unsigned emask) { return (__ballot_sync(kFull, p) & emask) != 0u; }
+
+// LDL^T solve with the symmetric matrix spread one column per lane: H[0..NV-1] = rows of this lane's column (full
+// column, both triangles), H[NV] = this lane's rhs entry.  Right-looking elimination; column k is left unscaled
+// (H[r][k] = l_rk d_k) so that each trailing update is one shuffle + one FMA.  Returns x for this lane's row.
 template <int NV, int G>
-__device__ __forceinline__ float chol_solve_cols(float (&H)[NV + 1], int l, unsigned gmask) {
+__device__ __forceinline__ float ldl_solve_cols(float (&H)[NV + 1], int l) {
   float invd = 0.f;
 #pragma unroll
   for (int k = 0; k < NV; k++) {
-    float dk = __shfl_sync(gmask, H[k], k, G);
-    float inv = rsqrtf(fmaxf(dk, 1e-30f));
-    float lck = H[k] * inv;                 // lanes c > k: L[c][k];  lane k: sqrt(dk)
-    const bool upd = l > k, isk = l == k;
-    if (isk) invd = inv;
+    const float dk = __shfl_sync(kFull, H[k], k, G);
+    const float inv = 1.f / fmaxf(dk, 1e-30f);
+    const float lck = H[k] * inv;          // lanes c > k: l_ck = H[c][k] / d_k (H is symmetric)
+    const bool upd = l > k;
+    if (l == k) invd = inv;
 #pragma unroll
     for (int r = k + 1; r <= NV; r++) {
-      float vr = __shfl_sync(gmask, H[r], k, G) * inv;   // L[r][k] (r == NV: forward-substituted rhs)
+      const float vr = __shfl_sync(kFull, H[r], k, G);     // H[r][k];  r == NV: forward-substituted rhs z_k
       if (upd) H[r] = fmaf(-vr, lck, H[r]);
-      if (isk) H[r] = vr;
     }
-    if (isk) H[k] = lck;
   }
-  // back substitution L^T x = y
-  float accv = H[NV], x = 0.f;
+  // x_c = (z_c - sum_{r>c} H[r][c] x_r) / d_c
+  float sacc = H[NV], x = 0.f;
 #pragma unroll
   for (int k = NV - 1; k >= 0; k--) {
-    float xk = __shfl_sync(gmask, accv * invd, k, G);
-    if (l < k) accv = fmaf(-H[k], xk, accv);
+    const float xk = __shfl_sync(kFull, sacc * invd, k, G);
+    if (l < k) sacc = fmaf(-H[k], xk, sacc);
     if (l == k) x = xk;
   }
   return x;
@@ -171,8 +186,8 @@ __device__ __forceinline__ float chol_solve_cols(float (&H)[NV + 1], int l, unsi
 // Kinematics of the tree for the joint configuration published in E.sn / E.cs: body frames relative to O and world
 // joint axes.  (mj_kinematics for hinge joints anchored at the body origin; root slides move O itself.)
 template <int G>
-__device__ __forceinline__ void tree_kinematics(const DevModel& M, EnvSmem<G>& E, const LaneConst& L) {
-  const int slot = L.l / 3, r = L.l - 3 * slot;
+__device__ __forceinline__ void tree_kinematics(const DevModel& M, EnvSmem<G>& E, int l) {
+  const int slot = l / 3, r = l - 3 * slot;
   for (int lev = 0; lev < M.nlevel; lev++) {
     if (slot < M.level_count[lev]) {
       const int b = M.level_body[lev][slot], p = M.body_parent[b];
@@ -198,27 +213,28 @@ __device__ __forceinline__ void tree_kinematics(const DevModel& M, EnvSmem<G>& E
       E.bodyR[b][3 * r] = R0; E.bodyR[b][3 * r + 1] = R1; E.bodyR[b][3 * r + 2] = R2;
       E.bodyR[b][9 + r] = pr;
     }
-    __syncwarp(L.gmask);
+    __syncwarp();
   }
 }
 
 // One forward-dynamics evaluation (mj_forward).  q, v: this lane's coordinates; a: warm start in, qacc out.
+// Must be called by all 32 lanes of the warp (warp-uniform control flow).
 template <int NV, int G, bool DBG>
 __device__ __forceinline__ void forward_dynamics(const DevModel& M, EnvSmem<G>& E, const LaneConst& L, float q,
-                                                 float v, float tau, float& a, Counters& cnt, float* dbg) {
+                                                 float v, float tau, float& a, ActiveSet& AS, Counters& cnt,
+                                                 float* dbg) {
   const int l = L.l;
-  const unsigned gmask = L.gmask;
   // ---- 1. publish joint trig + velocity -------------------------------------------------------------
   {
     float s = q - L.ref, c = 1.f;
     if (L.isdof && L.type == 1) sincosf(L.sign * (q - L.ref), &s, &c);
-    if (L.isdof) { E.sn[l] = s; E.cs[l] = c; E.v[l] = v; E.acc[l] = a; }
+    if (L.isdof) { E.sn[l] = s; E.cs[l] = c; E.v[l] = v; }
   }
-  __syncwarp(gmask);
+  __syncwarp();
   float zO = M.root_z0;
   for (int j = 0; j < M.nslide; j++) zO = fmaf(M.dof_slide_z[j], E.sn[j], zO);
   // ---- 2. body frames ----------------------------------------------------------------------------
-  tree_kinematics<G>(M, E, L);
+  tree_kinematics<G>(M, E, l);
   // ---- 3. motion vectors, body inertias about O ------------------------------------------------------
   Vec6 S = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   if (L.isdof) {
@@ -253,7 +269,7 @@ __device__ __forceinline__ void forward_dynamics(const DevModel& M, EnvSmem<G>& 
     *reinterpret_cast<float4*>(I + 4) = make_float4(Ixx, Ixy, Ixz, Iyy);
     *reinterpret_cast<float2*>(I + 8) = make_float2(Iyz, Izz);
   }
-  __syncwarp(gmask);
+  __syncwarp();
   // ---- 4. velocities (RNE forward), composite inertias -------------------------------------------------
   if (L.isdof) {
     Vec6 Vp = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -291,7 +307,7 @@ __device__ __forceinline__ void forward_dynamics(const DevModel& M, EnvSmem<G>& 
     *reinterpret_cast<float4*>(E.Ic[l] + 4) = a1;
     *reinterpret_cast<float2*>(E.Ic[l] + 8) = a2;
   }
-  __syncwarp(gmask);
+  __syncwarp();
   // ---- 5. body forces; contact candidates ---------------------------------------------------------------
   if (L.isbody) {
     Vec6 Ab = {0.f, 0.f, 0.f, 0.f, 0.f, -M.gravity_z};     // fictitious base acceleration = -gravity
@@ -316,6 +332,7 @@ __device__ __forceinline__ void forward_dynamics(const DevModel& M, EnvSmem<G>& 
   float cPx[kNPass], cPy[kNPass], cPz[kNPass], cD[kNPass], cmu[kNPass], car[kNPass][4];
   int cbody[kNPass];
   unsigned conmask = 0;
+  const int wl = threadIdx.x & 31;
 #pragma unroll
   for (int ps = 0; ps < kNPass; ps++) {
     const int s = ps * G + l;
@@ -348,9 +365,8 @@ __device__ __forceinline__ void forward_dynamics(const DevModel& M, EnvSmem<G>& 
       }
     }
     // plane-box keeps at most the first four penetrating corners (MuJoCo mjc_PlaneBox)
-    {
-      const unsigned bal = __ballot_sync(gmask, act && isbox);
-      const int wl = threadIdx.x & 31;
+    if (ps == 0) {
+      const unsigned bal = __ballot_sync(kFull, act && isbox);
       const unsigned seg = 0xFFu << (wl & ~7);
       const int rank = __popc(bal & seg & ((1u << wl) - 1u));
       if (isbox && rank >= 4) act = false;
@@ -377,8 +393,9 @@ __device__ __forceinline__ void forward_dynamics(const DevModel& M, EnvSmem<G>& 
       car[ps][3] = -M.Bc * (uz - mu * uy) + base;
     }
   }
-  __syncwarp(gmask);   // E.A complete
-  conmask = __reduce_or_sync(gmask, conmask);
+  __syncwarp();   // E.A complete
+  // bodies with a contact in either environment of the warp (W/U are kept valid for the union in both)
+  conmask = __reduce_or_sync(kFull, conmask);
   // ---- 6. bias force, smooth rhs, Ic*S ---------------------------------------------------------------------
   float rhs0 = 0.f;
   Vec6 Fdc = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -393,23 +410,18 @@ __device__ __forceinline__ void forward_dynamics(const DevModel& M, EnvSmem<G>& 
     st6(E.Fd[l], Fdc);     // safe: the cdd values in E.Fd were consumed before the last barrier
     if (DBG) { dbg[0 * 32 + l] = cb; dbg[1 * 32 + l] = rhs0; }
   }
-  __syncwarp(gmask);
+  __syncwarp();
   // ---- 7. mass-matrix column ---------------------------------------------------------------------------------
+  // M[r][c] = S_shallow . (Ic_deep S_deep): rows at or below this dof read Fd[r], rows above read S[r]
   float Mcol[NV];
+  const unsigned relmask = L.isdof ? (L.anc | L.desc | (1u << l)) : 0u;
 #pragma unroll
   for (int r = 0; r < NV; r++) {
-    float mv = 0.f;
-    if (L.isdof) {
-      if (r == l) {
-        mv = dot6(S, Fdc) + L.armature;
-      } else if ((L.desc >> r) & 1u) {
-        mv = dot6(S, ld6(E.Fd[r]));
-      } else if ((L.anc >> r) & 1u) {
-        mv = dot6(ld6(E.S[r]), Fdc);
-      }
-    } else if (r == l) {
-      mv = 1.f;
-    }
+    const bool deeper = r >= l;
+    const Vec6 x = ld6(deeper ? E.Fd[r] : E.S[r]);
+    const float d = deeper ? dot6(S, x) : dot6(Fdc, x);
+    float mv = ((relmask >> r) & 1u) ? d : 0.f;
+    if (r == l) mv += L.armature;
     Mcol[r] = mv;
     if (DBG) dbg[(2 + r) * 32 + l] = mv;
   }
@@ -425,147 +437,177 @@ __device__ __forceinline__ void forward_dynamics(const DevModel& M, EnvSmem<G>& 
       laref = -M.Bc * lsg * v - M.Kc * imp * dist;
     }
   }
-  const bool anylimit = __any_sync(gmask, lsg != 0.f);
   cnt.evals++;
+  // ---- 8. active-set iteration ----------------------------------------------------------------------------------
+  // The active set of the previous evaluation (same lane <-> same contact candidate) is the starting guess; a contact
+  // or limit that was not present before starts with all of its rows active.  Without any constraint in the warp the
+  // loop body runs once and is the plain solve M qacc = rhs0.
+#pragma unroll
+  for (int ps = 0; ps < kNPass; ps++) {
+    if (!cact[ps]) AS.bits[ps] = 0u;
+    else if (!((AS.prev_act >> ps) & 1u)) AS.bits[ps] = 0xFu;
+  }
+  if (lsg == 0.f) AS.lbit = false;
+  else if (!AS.prev_lim) AS.lbit = true;
+  const bool sph_any = __any_sync(kFull, cact[1]);
+  const bool constrained = (conmask != 0u) || __any_sync(kFull, lsg != 0.f);
+  const bool seg_any = __any_sync(kFull, cact[0]);
   float H[NV + 1];
-  if (conmask == 0u && !anylimit) {
-#pragma unroll
-    for (int r = 0; r < NV; r++) H[r] = Mcol[r];
-    H[NV] = rhs0;
-    a = chol_solve_cols<NV, G>(H, l, gmask);
-    if (!L.isdof) a = 0.f;
-    if (L.isdof) E.acc[l] = a;
-  } else {
-    // ---- 8. active-set iteration ------------------------------------------------------------------------------
-    unsigned bits[kNPass];
-    bool lbit;
-    auto eval_rows = [&](unsigned (&nb)[kNPass], bool& nl) {
-      if (L.isbody && ((conmask >> l) & 1u)) {
-        Vec6 Tb = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        for (unsigned mk = M.body_supp[l]; mk; mk &= mk - 1) {
-          const int i = __ffs(mk) - 1;
-          axpy6(Tb, E.acc[i], ld6(E.S[i]));
-        }
-        st6(E.T[l], Tb);
-      }
-      __syncwarp(gmask);
-#pragma unroll
-      for (int ps = 0; ps < kNPass; ps++) {
-        nb[ps] = 0u;
-        if (cact[ps]) {
-          const Vec6 Tb = ld6(E.T[cbody[ps]]);
-          float ux, uy, uz;
-          cross3(ux, uy, uz, Tb.w0, Tb.w1, Tb.w2, cPx[ps], cPy[ps], cPz[ps]);
-          ux += Tb.v0; uy += Tb.v1; uz += Tb.v2;
-          const float mu = cmu[ps];
-          nb[ps] = ((uz + mu * ux - car[ps][0] < 0.f) ? 1u : 0u) | ((uz - mu * ux - car[ps][1] < 0.f) ? 2u : 0u) |
-                   ((uz + mu * uy - car[ps][2] < 0.f) ? 4u : 0u) | ((uz - mu * uy - car[ps][3] < 0.f) ? 8u : 0u);
-        }
-      }
-      nl = (lsg != 0.f) && (lsg * a - laref < 0.f);
-    };
-    eval_rows(bits, lbit);
-    for (int it = 0; it < kMaxSolverIter; it++) {
+  for (int it = 0; it < kMaxSolverIter; it++) {
+    if (constrained) {
       cnt.iters++;
-      // zero the per-body accumulators
+      // zero the accumulators of every body in the union (an environment may have no contact on some of them)
       for (unsigned mk = conmask; mk; mk &= mk - 1) {
         const int b = __ffs(mk) - 1;
         for (int i = l; i < 24; i += G) E.W[b][i] = 0.f;
         if (l < 8) E.U[b][l] = 0.f;
       }
-      __syncwarp(gmask);
+      __syncwarp();
 #pragma unroll
       for (int ps = 0; ps < kNPass; ps++) {
-        if (cact[ps] && bits[ps]) {
+        if (ps == 0 ? !seg_any : !sph_any) continue;
+        // wrench-space Hessian of this contact's active pyramid rows: w = (P x d, d), W += D w w^T, U += D aref w
+        float wv[28];
+#pragma unroll
+        for (int i = 0; i < 28; i++) wv[i] = 0.f;
+        const unsigned bt = cact[ps] ? AS.bits[ps] : 0u;
+        if (bt) {
           const float D = cD[ps], mu = cmu[ps];
-          const float s0 = (bits[ps] & 1u) ? 1.f : 0.f, s1 = (bits[ps] & 2u) ? 1.f : 0.f;
-          const float s2 = (bits[ps] & 4u) ? 1.f : 0.f, s3 = (bits[ps] & 8u) ? 1.f : 0.f;
+          const float s0 = (bt & 1u) ? 1.f : 0.f, s1 = (bt & 2u) ? 1.f : 0.f;
+          const float s2 = (bt & 4u) ? 1.f : 0.f, s3 = (bt & 8u) ? 1.f : 0.f;
           const float Qxx = D * mu * mu * (s0 + s1), Qyy = D * mu * mu * (s2 + s3), Qzz = D * (s0 + s1 + s2 + s3);
           const float Qxz = D * mu * (s0 - s1), Qyz = D * mu * (s2 - s3);
           const float Px = cPx[ps], Py = cPy[ps], Pz = cPz[ps];
-          // X = [P]x Q  (rows), Q rows: (Qxx,0,Qxz) (0,Qyy,Qyz) (Qxz,Qyz,Qzz)
+          // X = [P]x Q with Q rows (Qxx,0,Qxz) (0,Qyy,Qyz) (Qxz,Qyz,Qzz);  Nn row i = P x X_i
           const float X00 = Py * Qxz, X01 = -Pz * Qyy + Py * Qyz, X02 = -Pz * Qyz + Py * Qzz;
           const float X10 = Pz * Qxx - Px * Qxz, X11 = -Px * Qyz, X12 = Pz * Qxz - Px * Qzz;
           const float X20 = -Py * Qxx, X21 = Px * Qyy, X22 = -Py * Qxz + Px * Qyz;
-          // Nn row i = P x X_i
-          float n00, n01, n02, n10, n11, n12, n20, n21, n22;
-          cross3(n00, n01, n02, Px, Py, Pz, X00, X01, X02);
-          cross3(n10, n11, n12, Px, Py, Pz, X10, X11, X12);
-          cross3(n20, n21, n22, Px, Py, Pz, X20, X21, X22);
-          (void)n10; (void)n20; (void)n21;
-          float* Wb = E.W[cbody[ps]];
-          atomicAdd(&Wb[sym6(0, 0)], n00); atomicAdd(&Wb[sym6(0, 1)], n01); atomicAdd(&Wb[sym6(0, 2)], n02);
-          atomicAdd(&Wb[sym6(1, 1)], n11); atomicAdd(&Wb[sym6(1, 2)], n12); atomicAdd(&Wb[sym6(2, 2)], n22);
-          atomicAdd(&Wb[sym6(0, 3)], X00); atomicAdd(&Wb[sym6(0, 4)], X01); atomicAdd(&Wb[sym6(0, 5)], X02);
-          atomicAdd(&Wb[sym6(1, 3)], X10); atomicAdd(&Wb[sym6(1, 4)], X11); atomicAdd(&Wb[sym6(1, 5)], X12);
-          atomicAdd(&Wb[sym6(2, 3)], X20); atomicAdd(&Wb[sym6(2, 4)], X21); atomicAdd(&Wb[sym6(2, 5)], X22);
-          atomicAdd(&Wb[sym6(3, 3)], Qxx); atomicAdd(&Wb[sym6(3, 5)], Qxz);
-          atomicAdd(&Wb[sym6(4, 4)], Qyy); atomicAdd(&Wb[sym6(4, 5)], Qyz); atomicAdd(&Wb[sym6(5, 5)], Qzz);
+          float t0, t1, t2;
+          cross3(wv[sym6(0, 0)], wv[sym6(0, 1)], wv[sym6(0, 2)], Px, Py, Pz, X00, X01, X02);
+          cross3(t0, wv[sym6(1, 1)], wv[sym6(1, 2)], Px, Py, Pz, X10, X11, X12);
+          cross3(t1, t2, wv[sym6(2, 2)], Px, Py, Pz, X20, X21, X22);
+          (void)t0; (void)t1; (void)t2;
+          wv[sym6(0, 3)] = X00; wv[sym6(0, 4)] = X01; wv[sym6(0, 5)] = X02;
+          wv[sym6(1, 3)] = X10; wv[sym6(1, 4)] = X11; wv[sym6(1, 5)] = X12;
+          wv[sym6(2, 3)] = X20; wv[sym6(2, 4)] = X21; wv[sym6(2, 5)] = X22;
+          wv[sym6(3, 3)] = Qxx; wv[sym6(3, 5)] = Qxz; wv[sym6(4, 4)] = Qyy; wv[sym6(4, 5)] = Qyz;
+          wv[sym6(5, 5)] = Qzz;
           const float a0 = s0 * car[ps][0], a1 = s1 * car[ps][1], a2 = s2 * car[ps][2], a3 = s3 * car[ps][3];
           const float gx = D * mu * (a0 - a1), gy = D * mu * (a2 - a3), gz = D * (a0 + a1 + a2 + a3);
-          float mx, my, mz;
-          cross3(mx, my, mz, Px, Py, Pz, gx, gy, gz);
-          float* Ub = E.U[cbody[ps]];
-          atomicAdd(&Ub[0], mx); atomicAdd(&Ub[1], my); atomicAdd(&Ub[2], mz);
-          atomicAdd(&Ub[3], gx); atomicAdd(&Ub[4], gy); atomicAdd(&Ub[5], gz);
+          cross3(wv[21], wv[22], wv[23], Px, Py, Pz, gx, gy, gz);
+          wv[24] = gx; wv[25] = gy; wv[26] = gz;
         }
-      }
-      __syncwarp(gmask);
-      // Hessian column
+        if (ps == 0) {
+          // pass 0 holds the box corners: the 8 lanes of a segment belong to one box = one body -> butterfly sum,
+          // then the segment adds its body's accumulators (a body may carry a box and a capsule -> atomics)
 #pragma unroll
-      for (int r = 0; r < NV; r++) H[r] = Mcol[r];
-      H[NV] = rhs0;
-      if (L.isdof) {
-        for (unsigned mk = conmask; mk; mk &= mk - 1) {
-          const int b = __ffs(mk) - 1;
-          const unsigned supp = M.body_supp[b];
-          if ((supp >> l) & 1u) {
-            float Wl[24];
+          for (int i = 0; i < 27; i++) {
+            float t = wv[i];
+            t += __shfl_xor_sync(kFull, t, 1);
+            t += __shfl_xor_sync(kFull, t, 2);
+            t += __shfl_xor_sync(kFull, t, 4);
+            wv[i] = t;
+          }
+          const unsigned segact = __ballot_sync(kFull, cact[0]);
+          if ((segact >> (wl & ~7)) & 0xFFu) {
+            const int sl = wl & 7, b = cbody[0];
 #pragma unroll
-            for (int i = 0; i < 24; i += 4) {
-              const float4 t = *reinterpret_cast<const float4*>(&E.W[b][i]);
-              Wl[i] = t.x; Wl[i + 1] = t.y; Wl[i + 2] = t.z; Wl[i + 3] = t.w;
-            }
-            const float Sv[6] = {S.w0, S.w1, S.w2, S.v0, S.v1, S.v2};
-            float y[6];
-#pragma unroll
-            for (int i = 0; i < 6; i++) {
-              float t = 0.f;
-#pragma unroll
-              for (int j = 0; j < 6; j++) t = fmaf(Wl[sym6(i, j)], Sv[j], t);
-              y[i] = t;
-            }
-            const Vec6 yv = {y[0], y[1], y[2], y[3], y[4], y[5]};
-            H[NV] += dot6(S, ld6(E.U[b]));
-#pragma unroll
-            for (int r = 0; r < NV; r++) {
-              if ((supp >> r) & 1u) H[r] += dot6(ld6(E.S[r]), yv);
+            for (int i = 0; i < 27; i++) {
+              if ((i & 7) == sl) {
+                float* dst = i < 21 ? &E.W[b][i] : &E.U[b][i - 21];
+                if (sph_any) atomicAdd(dst, wv[i]); else *dst = wv[i];
+              }
             }
           }
-        }
-        if (lbit) {
+        } else if (bt) {
+          float* Wb = E.W[cbody[ps]];
+          float* Ub = E.U[cbody[ps]];
 #pragma unroll
-          for (int r = 0; r < NV; r++)
-            if (r == l) H[r] += lD;
-          H[NV] += lD * lsg * laref;
+          for (int i = 0; i < 21; i++) atomicAdd(&Wb[i], wv[i]);
+#pragma unroll
+          for (int i = 0; i < 6; i++) atomicAdd(&Ub[i], wv[21 + i]);
         }
       }
-      a = chol_solve_cols<NV, G>(H, l, gmask);
-      if (!L.isdof) a = 0.f;
-      if (L.isdof) E.acc[l] = a;
-      __syncwarp(gmask);
-      unsigned nbits[kNPass];
-      bool nl;
-      eval_rows(nbits, nl);
-      bool changed = nl != lbit;
-#pragma unroll
-      for (int ps = 0; ps < kNPass; ps++) changed = changed || (nbits[ps] != bits[ps]);
-#pragma unroll
-      for (int ps = 0; ps < kNPass; ps++) bits[ps] = nbits[ps];
-      lbit = nl;
-      if (!__any_sync(gmask, changed)) break;
+      __syncwarp();
     }
+    // Hessian column
+#pragma unroll
+    for (int r = 0; r < NV; r++) H[r] = Mcol[r];
+    H[NV] = rhs0;
+    if (constrained && L.isdof) {
+      for (unsigned mk = conmask; mk; mk &= mk - 1) {
+        const int b = __ffs(mk) - 1;
+        const unsigned supp = M.body_supp[b];
+        if ((supp >> l) & 1u) {
+          float Wl[24];
+#pragma unroll
+          for (int i = 0; i < 24; i += 4) {
+            const float4 t = *reinterpret_cast<const float4*>(&E.W[b][i]);
+            Wl[i] = t.x; Wl[i + 1] = t.y; Wl[i + 2] = t.z; Wl[i + 3] = t.w;
+          }
+          const float Sv[6] = {S.w0, S.w1, S.w2, S.v0, S.v1, S.v2};
+          float y[6];
+#pragma unroll
+          for (int i = 0; i < 6; i++) {
+            float t = 0.f;
+#pragma unroll
+            for (int j = 0; j < 6; j++) t = fmaf(Wl[sym6(i, j)], Sv[j], t);
+            y[i] = t;
+          }
+          const Vec6 yv = {y[0], y[1], y[2], y[3], y[4], y[5]};
+          H[NV] += dot6(S, ld6(E.U[b]));
+#pragma unroll
+          for (int r = 0; r < NV; r++) {
+            if ((supp >> r) & 1u) H[r] += dot6(ld6(E.S[r]), yv);
+          }
+        }
+      }
+      if (AS.lbit) {
+#pragma unroll
+        for (int r = 0; r < NV; r++)
+          if (r == l) H[r] += lD;
+        H[NV] += lD * lsg * laref;
+      }
+    }
+    a = ldl_solve_cols<NV, G>(H, l);
+    if (!L.isdof) a = 0.f;
+    if (L.isdof) E.acc[l] = a;
+    if (!constrained) break;
+    __syncwarp();
+    // ---- re-evaluate the rows at the new qacc: J_i a = w_i . (S_b a) ----
+    if (L.isbody && ((conmask >> l) & 1u)) {
+      Vec6 Tb = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      for (unsigned mk = M.body_supp[l]; mk; mk &= mk - 1) {
+        const int i = __ffs(mk) - 1;
+        axpy6(Tb, E.acc[i], ld6(E.S[i]));
+      }
+      st6(E.T[l], Tb);
+    }
+    __syncwarp();
+    bool changed = false;
+#pragma unroll
+    for (int ps = 0; ps < kNPass; ps++) {
+      if (cact[ps]) {
+        const Vec6 Tb = ld6(E.T[cbody[ps]]);
+        float ux, uy, uz;
+        cross3(ux, uy, uz, Tb.w0, Tb.w1, Tb.w2, cPx[ps], cPy[ps], cPz[ps]);
+        ux += Tb.v0; uy += Tb.v1; uz += Tb.v2;
+        const float mu = cmu[ps];
+        const unsigned nb = ((uz + mu * ux - car[ps][0] < 0.f) ? 1u : 0u) | ((uz - mu * ux - car[ps][1] < 0.f) ? 2u : 0u) |
+                            ((uz + mu * uy - car[ps][2] < 0.f) ? 4u : 0u) | ((uz - mu * uy - car[ps][3] < 0.f) ? 8u : 0u);
+        changed = changed || (nb != AS.bits[ps]);
+        AS.bits[ps] = nb;
+      }
+    }
+    {
+      const bool nl = (lsg != 0.f) && (lsg * a - laref < 0.f);
+      changed = changed || (nl != AS.lbit);
+      AS.lbit = nl;
+    }
+    if (!__any_sync(kFull, changed)) break;
   }
+  AS.prev_act = (cact[0] ? 1u : 0u) | (cact[1] ? 2u : 0u);
+  AS.prev_lim = lsg != 0.f;
   if (DBG) {
     dbg[(2 + NV) * 32 + l] = a;
     if (l == 0) {
@@ -628,16 +670,17 @@ __device__ __forceinline__ void ref_lookup(const DevModel& M, const StepArgs& A,
   }
 }
 
+// sums / minima over the G lanes of an environment (xor offsets below G never leave the group)
 template <int G>
-__device__ __forceinline__ float group_sum(float x, unsigned gmask) {
+__device__ __forceinline__ float group_sum(float x) {
 #pragma unroll
-  for (int o = G / 2; o > 0; o >>= 1) x += __shfl_xor_sync(gmask, x, o, G);
+  for (int o = G / 2; o > 0; o >>= 1) x += __shfl_xor_sync(kFull, x, o);
   return x;
 }
 template <int G>
-__device__ __forceinline__ float group_min(float x, unsigned gmask) {
+__device__ __forceinline__ float group_min(float x) {
 #pragma unroll
-  for (int o = G / 2; o > 0; o >>= 1) x = fminf(x, __shfl_xor_sync(gmask, x, o, G));
+  for (int o = G / 2; o > 0; o >>= 1) x = fminf(x, __shfl_xor_sync(kFull, x, o));
   return x;
 }
 
@@ -690,21 +733,24 @@ __device__ __forceinline__ void build_obs(const DevModel& M, const StepArgs& A, 
     if (l >= 1) E.obsbuf[np + nd + l - 1] = q;
     E.obsbuf[np + nd + M.nv - 1 + l] = v;
   }
-  __syncwarp(L.gmask);
+  __syncwarp();
 }
 
+// obs (optionally mirrored, mimic_env.py:440-480) from E.obsbuf to global memory; `enable` predicates the stores
 template <int G>
-__device__ __forceinline__ void write_obs(const DevModel& M, EnvSmem<G>& E, const LaneConst& L, bool mirror,
+__device__ __forceinline__ void write_obs(const DevModel& M, EnvSmem<G>& E, int l, bool mirror, bool enable,
                                           float* __restrict__ dst) {
-  for (int k = L.l; k < M.obs_dim; k += G)
-    dst[k] = mirror ? M.mirror_obs_sign[k] * E.obsbuf[M.mirror_obs_idx[k]] : E.obsbuf[k];
-  __syncwarp(L.gmask);
+  if (enable)
+    for (int k = l; k < M.obs_dim; k += G)
+      dst[k] = mirror ? M.mirror_obs_sign[k] * E.obsbuf[M.mirror_obs_idx[k]] : E.obsbuf[k];
+  __syncwarp();
 }
 
-// MimicEnv.reset_model (mimic_env.py:526-572): RSI, ground-contact shift, refs.next(); leaves obs in E.obsbuf
+// MimicEnv.reset_model (mimic_env.py:526-572): RSI, ground-contact shift, refs.next().  Warp-uniform: every lane
+// computes a reset, the caller commits it only for environments that need one.
 template <int G>
-__device__ __forceinline__ void reset_env(const DevModel& M, const StepArgs& A, EnvSmem<G>& E, const LaneConst& L,
-                                          int env, Cursor& c, float& q, float& v, float& dist, float& zoff) {
+__device__ __noinline__ void reset_env(const DevModel& M, const StepArgs& A, EnvSmem<G>& E, const LaneConst& L,
+                                       int env, Cursor& c, float& q, float& v, float& dist, float& zoff) {
   const int l = L.l;
   c.ep_dur = 0;
   if (A.eval_mode) {                           // straight:237-265 / base:69-77
@@ -738,290 +784,297 @@ __device__ __forceinline__ void reset_env(const DevModel& M, const StepArgs& A, 
     if (L.isdof && L.type == 1) sincosf(L.sign * (q - L.ref), &s, &cc);
     if (L.isdof) { E.sn[l] = s; E.cs[l] = cc; }
   }
-  __syncwarp(L.gmask);
+  __syncwarp();
   float zO = M.root_z0;
   for (int j = 0; j < M.nslide; j++) zO = fmaf(M.dof_slide_z[j], E.sn[j], zO);
-  tree_kinematics<G>(M, E, L);
+  tree_kinematics<G>(M, E, l);
   float sz = 3.0e38f;
   for (int s = l; s < M.nsite; s += G) {
     const float* R = E.bodyR[M.site_body[s]];
     sz = fminf(sz, zO + R[11] + R[6] * M.site_pos[s][0] + R[7] * M.site_pos[s][1] + R[8] * M.site_pos[s][2]);
   }
-  const float lowest = group_min<G>(sz, L.gmask);
+  const float lowest = group_min<G>(sz);
   if (l == M.com_z_dof) q -= lowest;
   zoff = lowest;                               // refs.adjust_COM_Z_pos(lowest)
   cursor_next(M, A, c, dist);                  // mimic_env.py:568
-  __syncwarp(L.gmask);
+  __syncwarp();
 }
 
-template <int NV, int G, bool DBG>
+template <int NV, int G, bool RK4, bool DBG>
 __global__ void __launch_bounds__(128) mimic_step_kernel(const StepArgs A, const int do_reset_only) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   DevModel& M = *reinterpret_cast<DevModel*>(smem_raw);
   constexpr int kModelBytes = (sizeof(DevModel) + 15) / 16 * 16;
   EnvSmem<G>* envs = reinterpret_cast<EnvSmem<G>*>(smem_raw + kModelBytes);
-  __shared__ double blk_stats[DRL_STATS_COUNT];
   {
-    const int* src = reinterpret_cast<const int*>(A.model);
-    int* dst = reinterpret_cast<int*>(smem_raw);
-    for (int i = threadIdx.x; i < (int)(sizeof(DevModel) / 4); i += blockDim.x) dst[i] = src[i];
-    if (threadIdx.x < DRL_STATS_COUNT) blk_stats[threadIdx.x] = 0.0;
+    const int4* src = reinterpret_cast<const int4*>(A.model);
+    int4* dst = reinterpret_cast<int4*>(smem_raw);
+    for (int i = threadIdx.x; i < (int)(sizeof(DevModel) / 16); i += blockDim.x) dst[i] = src[i];
   }
   __syncthreads();
   const int epb = blockDim.x / G;
   const int eib = threadIdx.x / G;
-  const int env = blockIdx.x * epb + eib;
-  const bool env_valid = env < A.num_envs;
-  if (env_valid) {
-    EnvSmem<G>& E = envs[eib];
-    LaneConst L;
-    L.l = threadIdx.x % G;
-    const int l = L.l;
-    L.gmask = (G == 32) ? 0xFFFFFFFFu : (0xFFFFu << (16 * ((threadIdx.x & 31) / 16)));
-    L.isdof = l < M.nv;
-    L.isbody = l < M.nb;
-    const int jd = L.isdof ? l : 0;
-    L.body = M.dof_body[jd]; L.type = M.dof_type[jd]; L.limited = M.dof_limited[jd]; L.last = M.dof_last[jd];
-    L.sign = M.dof_sign[jd]; L.ref = M.dof_ref[jd]; L.damping = M.dof_damping[jd]; L.armature = M.dof_armature[jd];
-    L.lo = M.dof_lo[jd]; L.hi = M.dof_hi[jd]; L.invw = M.dof_invw[jd];
-    L.anc = M.dof_anc[jd]; L.desc = M.dof_desc[jd]; L.subb = M.dof_subbodies[jd];
-    const unsigned gmask = L.gmask;
+  const int env_raw = blockIdx.x * epb + eib;
+  // a warp whose second environment is past the end recomputes the last valid one with all stores disabled
+  const bool live = env_raw < A.num_envs;
+  const int env = live ? env_raw : A.num_envs - 1;
+  if (blockIdx.x * epb + (threadIdx.x & ~31) / G >= A.num_envs) return;   // whole warp out of range
+  EnvSmem<G>& E = envs[eib];
+  LaneConst L;
+  L.l = threadIdx.x % G;
+  const int l = L.l;
+  L.emask = (G == 32) ? kFull : (0xFFFFu << (16 * ((threadIdx.x & 31) / 16)));
+  L.isdof = l < M.nv;
+  L.isbody = l < M.nb;
+  const int jd = L.isdof ? l : 0;
+  L.body = M.dof_body[jd]; L.type = M.dof_type[jd]; L.limited = M.dof_limited[jd]; L.last = M.dof_last[jd];
+  L.sign = M.dof_sign[jd]; L.ref = M.dof_ref[jd]; L.damping = M.dof_damping[jd]; L.armature = M.dof_armature[jd];
+  L.lo = M.dof_lo[jd]; L.hi = M.dof_hi[jd]; L.invw = M.dof_invw[jd];
+  L.anc = M.dof_anc[jd]; L.desc = M.dof_desc[jd]; L.subb = M.dof_subbodies[jd];
 
-    float* sf = A.state_f + (size_t)env * (4 * G);
-    int* si = A.state_i + (size_t)env * kCurCount8;
-    float q = sf[l], v = sf[G + l], a = sf[2 * G + l];
-    Cursor c;
-    c.i_step = si[kCurIstep]; c.pos = si[kCurPos]; c.count = si[kCurCount]; c.ep_dur = si[kCurEpDur];
-    c.rsi_step = si[kCurRsiStep]; c.n_det = si[kCurNDet]; c.resets = si[kCurResets]; c.flags = si[kCurFlags];
-    float dist = sf[3 * G + kMiscDist], zoff = sf[3 * G + kMiscZoff];
-    Counters cnt = {0, 0};
+  float* sf = A.state_f + (size_t)env * (4 * G);
+  int* si = A.state_i + (size_t)env * kCurCount8;
+  float q = sf[l], v = sf[G + l], a = sf[2 * G + l];
+  Cursor c;
+  c.i_step = si[kCurIstep]; c.pos = si[kCurPos]; c.count = si[kCurCount]; c.ep_dur = si[kCurEpDur];
+  c.rsi_step = si[kCurRsiStep]; c.n_det = si[kCurNDet]; c.resets = si[kCurResets]; c.flags = si[kCurFlags];
+  float dist = sf[3 * G + kMiscDist], zoff = sf[3 * G + kMiscZoff];
+  Counters cnt = {0, 0};
+  ActiveSet AS = {{0u, 0u}, 0u, false, false};
+  float* obs_out = A.obs + (size_t)env * M.obs_dim;
 
-    if (do_reset_only) {
-      // VecEnv.reset(): (masked) reset of the episode state
-      if (A.reset_mask == nullptr || A.reset_mask[env]) {
-        reset_env<G>(M, A, E, L, env, c, q, v, dist, zoff);
-        a = 0.f;
-        float ph, dv;
-        build_obs<G>(M, A, E, L, c, q, v, ph, dv);
-        const bool left = M.mirror_policy && A.left_step[c.i_step];
-        write_obs<G>(M, E, L, left, A.obs + (size_t)env * M.obs_dim);
-        sf[l] = q; sf[G + l] = v; sf[2 * G + l] = 0.f;
-        if (l == 0) {
-          sf[3 * G + kMiscDist] = dist; sf[3 * G + kMiscZoff] = zoff;
-          sf[3 * G + kMiscWalked] = 0.f; sf[3 * G + kMiscEpRet] = 0.f; sf[3 * G + kMiscEpTor] = 0.f;
-          sf[3 * G + kMiscPrevPos] = 1.f; sf[3 * G + kMiscPrevVel] = 1.f; sf[3 * G + kMiscPrevCom] = 1.f;
-          si[kCurIstep] = c.i_step; si[kCurPos] = c.pos; si[kCurCount] = c.count; si[kCurEpDur] = 0;
-          si[kCurRsiStep] = c.rsi_step; si[kCurNDet] = c.n_det; si[kCurResets] = c.resets;
-        }
-      }
-    } else {
-      // ---- actions -> joint torques (mimic_env.py:170-192, :483-489; MuJoCo ctrl/force clamps) -----------------
-      const bool left0 = M.mirror_policy && A.left_step[c.i_step];
-      float force = 0.f;
-      {
-        float sc = 0.f;
-        if (l < M.nu) {
-          float act = A.actions[(size_t)env * M.act_dim + l];
-          act = fminf(fmaxf(act, -1.f), 1.f);
-          sc = act > 0.f ? __fmul_rn(act, M.act_chi[l]) : __fmul_rn(fabsf(act), M.act_clo[l]);
-        }
-        if (left0) {
-          const int src = l < M.nu ? M.mirror_act_idx[l] : 0;
-          const float o = __shfl_sync(gmask, sc, src, G);
-          sc = l < M.nu ? M.mirror_act_sign[l] * o : 0.f;
-        }
-        E.tau[l] = 0.f;
-        __syncwarp(gmask);
-        if (l < M.nu) {
-          const float cc = fminf(fmaxf(sc, M.act_clo[l]), M.act_chi[l]);
-          force = fminf(fmaxf(M.act_gear[l] * cc, M.act_flo[l]), M.act_fhi[l]);
-          E.tau[M.act_dof[l]] = M.act_gear[l] * force;
-        }
-        __syncwarp(gmask);
-      }
-      const float tau = E.tau[l];
-      const float mean_abs_torque = group_sum<G>(l < M.nu ? fabsf(force) : 0.f, gmask) / (float)M.nu;
-
-      // ---- physics: frame_skip x (RK4 | semi-implicit Euler) -----------------------------------------------------
-      const float h = M.timestep;
-      bool bad = false;
-      for (int sub = 0; sub < A.frame_skip; sub++) {
-        {
-          const bool b0 = !(fabsf(q) <= 1e10f) || !(fabsf(v) <= 1e10f);
-          if (__any_sync(gmask, L.isdof && b0)) { bad = true; break; }
-        }
-        if (M.integrator == DRL_INTEGRATOR_RK4) {
-          const float q0 = q, v0 = v;
-          float accq = 0.f, accv = 0.f;
-#pragma unroll 1
-          for (int st = 0; st < 4; st++) {
-            forward_dynamics<NV, G, DBG>(M, E, L, q, v, tau, a, cnt, A.debug ? A.debug + (size_t)env * 32 * 40 : nullptr);
-            const float bw = (st == 0 || st == 3) ? (1.f / 6.f) : (1.f / 3.f);
-            accq = fmaf(bw, v, accq);
-            accv = fmaf(bw, a, accv);
-            if (st < 3) {
-              const float aw = st == 2 ? 1.f : 0.5f;
-              const float vn = fmaf(h * aw, a, v0);
-              q = fmaf(h * aw, v, q0);
-              v = vn;
-            }
-          }
-          q = fmaf(h, accq, q0);
-          v = fmaf(h, accv, v0);
-        } else {
-          forward_dynamics<NV, G, DBG>(M, E, L, q, v, tau, a, cnt, A.debug ? A.debug + (size_t)env * 32 * 40 : nullptr);
-          // mj_Euler with implicit joint damping: (M + h B) a' = M a   [M a = tau_total + J'f]
-          // the Hessian column of M is rebuilt from E.S / E.Fd which are still valid
-          __syncwarp(gmask);   // E.acc holds the constrained qacc of every dof
-          float Hc[NV + 1];
-          float Ma = 0.f;
-          Vec6 S = L.isdof ? ld6(E.S[l]) : Vec6{0, 0, 0, 0, 0, 0};
-          Vec6 Fdc = L.isdof ? ld6(E.Fd[l]) : Vec6{0, 0, 0, 0, 0, 0};
-#pragma unroll
-          for (int r = 0; r < NV; r++) {
-            float mv = 0.f;
-            if (L.isdof) {
-              if (r == l) mv = dot6(S, Fdc) + L.armature;
-              else if ((L.desc >> r) & 1u) mv = dot6(S, ld6(E.Fd[r]));
-              else if ((L.anc >> r) & 1u) mv = dot6(ld6(E.S[r]), Fdc);
-              Ma = fmaf(mv, E.acc[r], Ma);
-              if (r == l) mv += h * L.damping;
-            } else if (r == l) {
-              mv = 1.f;
-            }
-            Hc[r] = mv;
-          }
-          Hc[NV] = Ma;
-          float an = chol_solve_cols<NV, G>(Hc, l, gmask);
-          if (!L.isdof) an = 0.f;
-          v = fmaf(h, an, v);
-          q = fmaf(h, v, q);
-        }
-      }
-      if (!bad) {
-        const bool b0 = !(fabsf(q) <= 1e10f) || !(fabsf(v) <= 1e10f);
-        bad = __any_sync(gmask, L.isdof && b0);
-      }
-
-      // ---- environment logic ------------------------------------------------------------------------------------
-      float walked = sf[3 * G + kMiscWalked];
-      float ep_ret = sf[3 * G + kMiscEpRet], ep_tor = sf[3 * G + kMiscEpTor];
-      float pos_rew = sf[3 * G + kMiscPrevPos], vel_rew = sf[3 * G + kMiscPrevVel], com_rew = sf[3 * G + kMiscPrevCom];
-      float reward = 0.f, phase0 = 0.f, des0 = 0.f;
-      bool done;
-      float* obs_out = A.obs + (size_t)env * M.obs_dim;
-      if (bad) {
-        // MujocoException path (mimic_env.py:86-91): reset, reward 0, done; the VecEnv then resets again (Q19),
-        // here a single reset serves both; the terminal observation is the post-reset observation as in the reference
-        done = true;
-        reward = 0.f;
-      } else {
-        cursor_next(M, A, c, dist);                                   // mimic_env.py:96
-        build_obs<G>(M, A, E, L, c, q, v, phase0, des0);               // mimic_env.py:99
-        c.ep_dur += 1;                                                // mimic_env.py:106
-        {                                                             // mimic_env.py:131-139
-          const float vx = __shfl_sync(gmask, v, 0, G), vy = __shfl_sync(gmask, v, 1, G);
-          const float cx = fminf(fmaxf(vx, -5.5f), 5.5f), cy = fminf(fmaxf(vy, -5.5f), 5.5f);
-          walked += sqrtf(cx * cx + cy * cy) * M.ctrl_freq_inv;
-        }
-        const float comz = __shfl_sync(gmask, q, M.com_z_dof, G);
-        const bool timeout = c.ep_dur >= M.ep_dur_max;
-        done = (comz < M.fall_z) || timeout;                          // mimic_env.py:113-120
-        if (done) {
-          reward = timeout ? 0.f : -0.f;                              // _get_ET_reward always evaluates to +-0 (Q1)
-        } else {
-          float rq, rv;
-          ref_lookup(M, A, c, dist, zoff, l, G, L.isdof, rq, rv);
-          const float dq = L.isdof ? q - rq : 0.f, dv = L.isdof ? v - rv : 0.f;
-          const bool iscom = (M.com_mask >> l) & 1u;
-          const float sp = group_sum<G>(iscom ? 0.f : dq * dq, gmask);
-          const float sv = group_sum<G>(iscom ? 0.f : dv * dv, gmask);
-          const float sc = group_sum<G>(iscom ? dq * dq : 0.f, gmask);
-          pos_rew = expf(-3.f * sp);                                  // mimic_env.py:592-622
-          vel_rew = expf(-0.05f * sv);
-          com_rew = expf(-16.f * sc);
-          reward = (M.w_pos * pos_rew + M.w_vel * vel_rew + M.w_com * com_rew) * M.rew_scale + M.alive_bonus;
-        }
-        const bool left1 = M.mirror_policy && A.left_step[c.i_step];
-        write_obs<G>(M, E, L, left1, (done && A.terminal_obs) ? A.terminal_obs + (size_t)env * M.obs_dim : obs_out);
-      }
-      // ---- Monitor.step (monitor_wrapper.py:88-166) ----------------------------------------------------------------
-      ep_ret += reward;
-      ep_tor += mean_abs_torque;
-      double* sd = A.state_d + (size_t)env * 4;
+  if (do_reset_only) {
+    // VecEnv.reset(): (masked) reset of the episode state
+    const bool want = live && (A.reset_mask == nullptr || A.reset_mask[env]);
+    if (!__any_sync(kFull, want)) return;
+    reset_env<G>(M, A, E, L, env, c, q, v, dist, zoff);
+    float ph, dv;
+    build_obs<G>(M, A, E, L, c, q, v, ph, dv);
+    const bool left = M.mirror_policy && A.left_step[c.i_step];
+    write_obs<G>(M, E, l, left, want, obs_out);
+    if (want) {
+      sf[l] = q; sf[G + l] = v; sf[2 * G + l] = 0.f;
       if (l == 0) {
-        sd[0] += (double)pos_rew; sd[1] += (double)vel_rew; sd[2] += (double)com_rew; sd[3] += 1.0;
-        atomicAdd(&blk_stats[DRL_STAT_ENV_STEPS], 1.0);
-        atomicAdd(&blk_stats[DRL_STAT_POS_REW_SUM], (double)pos_rew);
-        atomicAdd(&blk_stats[DRL_STAT_VEL_REW_SUM], (double)vel_rew);
-        atomicAdd(&blk_stats[DRL_STAT_COM_REW_SUM], (double)com_rew);
-        atomicAdd(&blk_stats[DRL_STAT_REW_STEPS], 1.0);
-        atomicAdd(&blk_stats[DRL_STAT_ABS_TORQUE_SUM], (double)mean_abs_torque);
-        atomicAdd(&blk_stats[DRL_STAT_SOLVER_ITERS], (double)cnt.iters);
-        atomicAdd(&blk_stats[DRL_STAT_DYN_EVALS], (double)cnt.evals);
-      }
-      if (A.extras && l == 0) {
-        float* ex = A.extras + (size_t)env * 16;
-        ex[0] = pos_rew; ex[1] = vel_rew; ex[2] = com_rew; ex[3] = walked; ex[4] = mean_abs_torque;
-        ex[5] = des0; ex[6] = phase0; ex[7] = zoff;
-      }
-      if (done) {
-        const int ep_len = bad ? c.ep_dur + 1 : c.ep_dur;
-        if (l == 0) {
-          float* ms = sf + 3 * G;
-          const int fl = c.flags;
-          auto smooth = [&](int slot, int bit, float nv, float f) {
-            ms[slot] = (fl >> bit) & 1 ? f * nv + (1.f - f) * ms[slot] : nv;   // utils.py:312-329
-          };
-          if (ep_len > 1) { smooth(kMiscMeanRewSm, 0, ep_ret / (float)(ep_len - 1), 0.9f); c.flags |= 1; }
-          smooth(kMiscPosSm, 1, (float)(sd[0] / sd[3]), 0.9f);
-          smooth(kMiscVelSm, 1, (float)(sd[1] / sd[3]), 0.9f);
-          smooth(kMiscComSm, 1, (float)(sd[2] / sd[3]), 0.9f);
-          smooth(kMiscEpRetSm, 1, ep_ret, 0.25f);
-          smooth(kMiscEpLenSm, 1, (float)ep_len, 0.75f);
-          smooth(kMiscTorSm, 1, ep_tor / (float)ep_len, 0.75f);
-          c.flags |= 2;
-          ms[kMiscMoved] = walked;
-          atomicAdd(&blk_stats[DRL_STAT_EPISODES], 1.0);
-          atomicAdd(&blk_stats[DRL_STAT_EP_LEN_SUM], (double)ep_len);
-          atomicAdd(&blk_stats[DRL_STAT_EP_RET_SUM], (double)ep_ret);
-          if (ep_len > 1) atomicAdd(&blk_stats[DRL_STAT_EP_MEAN_REW_SUM], (double)(ep_ret / (float)(ep_len - 1)));
-          atomicAdd(&blk_stats[DRL_STAT_MOVED_DISTANCE_SUM], (double)walked);
-          atomicAdd(&blk_stats[bad ? DRL_STAT_BLOWUPS : (c.ep_dur >= M.ep_dur_max ? DRL_STAT_TIMEOUTS : DRL_STAT_FALLS)], 1.0);
-          if (A.ring_cap > 0) {
-            const unsigned long long slot = atomicAdd(A.ring_head, 1ull) % (unsigned long long)A.ring_cap;
-            A.ring_len[slot] = ep_len;
-            A.ring_ret[slot] = ep_ret;
-          }
-        }
-        c.flags = __shfl_sync(gmask, c.flags, 0, G);
-        // ---- auto-reset (DummyVecEnv.step_wait) ----
-        reset_env<G>(M, A, E, L, env, c, q, v, dist, zoff);
-        a = 0.f;
-        walked = 0.f; ep_ret = 0.f; ep_tor = 0.f;
-        pos_rew = vel_rew = com_rew = 1.f;      // get_imitation_reward() inside reset_model (mimic_env.py:562)
-        float ph, dv;
-        build_obs<G>(M, A, E, L, c, q, v, ph, dv);
-        const bool left2 = M.mirror_policy && A.left_step[c.i_step];
-        write_obs<G>(M, E, L, left2, obs_out);
-        if (bad && A.terminal_obs) write_obs<G>(M, E, L, left2, A.terminal_obs + (size_t)env * M.obs_dim);
-      }
-      // ---- store ---------------------------------------------------------------------------------------------------
-      sf[l] = q; sf[G + l] = v; sf[2 * G + l] = a;
-      if (l == 0) {
-        A.rew[env] = reward;
-        A.done[env] = done ? 1 : 0;
-        float* ms = sf + 3 * G;
-        ms[kMiscDist] = dist; ms[kMiscZoff] = zoff; ms[kMiscWalked] = walked; ms[kMiscEpRet] = ep_ret;
-        ms[kMiscEpTor] = ep_tor; ms[kMiscPrevPos] = pos_rew; ms[kMiscPrevVel] = vel_rew; ms[kMiscPrevCom] = com_rew;
-        si[kCurIstep] = c.i_step; si[kCurPos] = c.pos; si[kCurCount] = c.count; si[kCurEpDur] = c.ep_dur;
-        si[kCurRsiStep] = c.rsi_step; si[kCurNDet] = c.n_det; si[kCurResets] = c.resets; si[kCurFlags] = c.flags;
+        sf[3 * G + kMiscDist] = dist; sf[3 * G + kMiscZoff] = zoff;
+        sf[3 * G + kMiscWalked] = 0.f; sf[3 * G + kMiscEpRet] = 0.f; sf[3 * G + kMiscEpTor] = 0.f;
+        sf[3 * G + kMiscPrevPos] = 1.f; sf[3 * G + kMiscPrevVel] = 1.f; sf[3 * G + kMiscPrevCom] = 1.f;
+        si[kCurIstep] = c.i_step; si[kCurPos] = c.pos; si[kCurCount] = c.count; si[kCurEpDur] = 0;
+        si[kCurRsiStep] = c.rsi_step; si[kCurNDet] = c.n_det; si[kCurResets] = c.resets;
       }
     }
+    return;
   }
-  __syncthreads();
-  if (!do_reset_only && threadIdx.x < DRL_STATS_COUNT && blk_stats[threadIdx.x] != 0.0)
-    atomicAdd(&A.stats[threadIdx.x], blk_stats[threadIdx.x]);
+
+  // ---- actions -> joint torques (mimic_env.py:170-192, :483-489; MuJoCo ctrl/force clamps) ---------------------
+  const bool left0 = M.mirror_policy && A.left_step[c.i_step];
+  float force = 0.f;
+  {
+    float sc = 0.f;
+    if (l < M.nu) {
+      float act = A.actions[(size_t)env * M.act_dim + l];
+      act = fminf(fmaxf(act, -1.f), 1.f);
+      sc = act > 0.f ? __fmul_rn(act, M.act_chi[l]) : __fmul_rn(fabsf(act), M.act_clo[l]);
+    }
+    {
+      const int src = l < M.nu ? M.mirror_act_idx[l] : 0;
+      const float o = __shfl_sync(kFull, sc, src, G);
+      if (left0) sc = l < M.nu ? M.mirror_act_sign[l] * o : 0.f;
+    }
+    E.tau[l] = 0.f;
+    __syncwarp();
+    if (l < M.nu) {
+      const float cc = fminf(fmaxf(sc, M.act_clo[l]), M.act_chi[l]);
+      force = fminf(fmaxf(M.act_gear[l] * cc, M.act_flo[l]), M.act_fhi[l]);
+      E.tau[M.act_dof[l]] = M.act_gear[l] * force;
+    }
+    __syncwarp();
+  }
+  const float tau = E.tau[l];
+  const float mean_abs_torque = group_sum<G>(l < M.nu ? fabsf(force) : 0.f) / (float)M.nu;
+
+  // ---- physics: frame_skip x (RK4 | semi-implicit Euler) ---------------------------------------------------------
+  const float h = M.timestep;
+  bool bad = false;      // MuJoCo's mj_checkPos / mj_checkVel: non-finite or huge state -> MujocoException
+  float* dbgp = (DBG && A.debug) ? A.debug + (size_t)env * 32 * 40 : nullptr;
+  for (int sub = 0; sub < A.frame_skip; sub++) {
+    bad = bad || env_any(L.isdof && (!(fabsf(q) <= 1e10f) || !(fabsf(v) <= 1e10f)), L.emask);
+    if (bad) { q = L.ref; v = 0.f; a = 0.f; }      // park the environment on a harmless state; it resets below
+    if (RK4) {
+      const float q0 = q, v0 = v;
+      float accq = 0.f, accv = 0.f;
+#pragma unroll 1
+      for (int st = 0; st < 4; st++) {
+        forward_dynamics<NV, G, DBG>(M, E, L, q, v, tau, a, AS, cnt, dbgp);
+        const float bw = (st == 0 || st == 3) ? (1.f / 6.f) : (1.f / 3.f);
+        accq = fmaf(bw, v, accq);
+        accv = fmaf(bw, a, accv);
+        if (st < 3) {
+          const float aw = st == 2 ? 1.f : 0.5f;
+          const float vn = fmaf(h * aw, a, v0);
+          q = fmaf(h * aw, v, q0);
+          v = vn;
+        }
+      }
+      q = fmaf(h, accq, q0);
+      v = fmaf(h, accv, v0);
+    } else {
+      forward_dynamics<NV, G, DBG>(M, E, L, q, v, tau, a, AS, cnt, dbgp);
+      // mj_Euler with implicit joint damping: (M + h B) a' = M a   [M a = tau_total + J'f]
+      // the column of M is rebuilt from E.S / E.Fd which are still valid
+      __syncwarp();   // E.acc holds the constrained qacc of every dof
+      float Hc[NV + 1];
+      float Ma = 0.f;
+      const Vec6 S = L.isdof ? ld6(E.S[l]) : Vec6{0, 0, 0, 0, 0, 0};
+      const Vec6 Fdc = L.isdof ? ld6(E.Fd[l]) : Vec6{0, 0, 0, 0, 0, 0};
+      const unsigned relmask = L.isdof ? (L.anc | L.desc | (1u << l)) : 0u;
+#pragma unroll
+      for (int r = 0; r < NV; r++) {
+        const bool deeper = r >= l;
+        const Vec6 x = ld6(deeper ? E.Fd[r] : E.S[r]);
+        const float d = deeper ? dot6(S, x) : dot6(Fdc, x);
+        float mv = ((relmask >> r) & 1u) ? d : 0.f;
+        if (r == l) mv += L.armature;
+        Ma = fmaf(mv, E.acc[r], Ma);
+        if (r == l) mv += h * L.damping;
+        Hc[r] = mv;
+      }
+      Hc[NV] = Ma;
+      float an = ldl_solve_cols<NV, G>(Hc, l);
+      if (!L.isdof) an = 0.f;
+      v = fmaf(h, an, v);
+      q = fmaf(h, v, q);
+    }
+  }
+  bad = bad || env_any(L.isdof && (!(fabsf(q) <= 1e10f) || !(fabsf(v) <= 1e10f)), L.emask);
+  if (bad) { q = L.ref; v = 0.f; a = 0.f; }
+
+  // ---- environment logic (computed for every lane; the blow-up path overrides the outcome) ------------------------
+  float walked = sf[3 * G + kMiscWalked];
+  float ep_ret = sf[3 * G + kMiscEpRet], ep_tor = sf[3 * G + kMiscEpTor];
+  float pos_rew = sf[3 * G + kMiscPrevPos], vel_rew = sf[3 * G + kMiscPrevVel], com_rew = sf[3 * G + kMiscPrevCom];
+  float reward, phase0 = 0.f, des0 = 0.f;
+  bool done;
+  const int ep_dur_before = c.ep_dur;
+  cursor_next(M, A, c, dist);                                   // mimic_env.py:96
+  build_obs<G>(M, A, E, L, c, q, v, phase0, des0);               // mimic_env.py:99
+  c.ep_dur += 1;                                                // mimic_env.py:106
+  {                                                             // mimic_env.py:131-139
+    const float vx = __shfl_sync(kFull, v, 0, G), vy = __shfl_sync(kFull, v, 1, G);
+    const float cx = fminf(fmaxf(vx, -5.5f), 5.5f), cy = fminf(fmaxf(vy, -5.5f), 5.5f);
+    walked += sqrtf(cx * cx + cy * cy) * M.ctrl_freq_inv;
+  }
+  const float comz = __shfl_sync(kFull, q, M.com_z_dof, G);
+  const bool timeout = c.ep_dur >= M.ep_dur_max;
+  done = (comz < M.fall_z) || timeout;                          // mimic_env.py:113-120
+  {
+    float rq, rv;
+    ref_lookup(M, A, c, dist, zoff, l, G, L.isdof, rq, rv);
+    const float dq = L.isdof ? q - rq : 0.f, dv = L.isdof ? v - rv : 0.f;
+    const bool iscom = (M.com_mask >> l) & 1u;
+    const float sp = group_sum<G>(iscom ? 0.f : dq * dq);
+    const float sv = group_sum<G>(iscom ? 0.f : dv * dv);
+    const float sc = group_sum<G>(iscom ? dq * dq : 0.f);
+    if (!done && !bad) {
+      pos_rew = expf(-3.f * sp);                                // mimic_env.py:592-622
+      vel_rew = expf(-0.05f * sv);
+      com_rew = expf(-16.f * sc);
+    }
+  }
+  if (bad) {
+    // MujocoException path (mimic_env.py:86-91): reset, reward 0, done; the VecEnv then resets again (Q19) — here a
+    // single reset serves both, and the terminal observation is the post-reset observation as in the reference
+    done = true;
+    reward = 0.f;
+  } else if (done) {
+    reward = timeout ? 0.f : -0.f;                              // _get_ET_reward always evaluates to +-0 (Q1)
+  } else {
+    reward = (M.w_pos * pos_rew + M.w_vel * vel_rew + M.w_com * com_rew) * M.rew_scale + M.alive_bonus;
+  }
+  {
+    const bool left1 = M.mirror_policy && A.left_step[c.i_step];
+    float* dst = (done && A.terminal_obs) ? A.terminal_obs + (size_t)env * M.obs_dim : obs_out;
+    write_obs<G>(M, E, l, left1, live && !bad, dst);
+  }
+  // ---- Monitor.step (monitor_wrapper.py:88-166) --------------------------------------------------------------------
+  ep_ret += reward;
+  ep_tor += mean_abs_torque;
+  double* sd = A.state_d + (size_t)env * 4;
+  if (l == 0 && live) {
+    sd[0] += (double)pos_rew; sd[1] += (double)vel_rew; sd[2] += (double)com_rew; sd[3] += 1.0;
+    atomicAdd(&A.stats[DRL_STAT_ENV_STEPS], 1.0);
+    atomicAdd(&A.stats[DRL_STAT_POS_REW_SUM], (double)pos_rew);
+    atomicAdd(&A.stats[DRL_STAT_VEL_REW_SUM], (double)vel_rew);
+    atomicAdd(&A.stats[DRL_STAT_COM_REW_SUM], (double)com_rew);
+    atomicAdd(&A.stats[DRL_STAT_REW_STEPS], 1.0);
+    atomicAdd(&A.stats[DRL_STAT_ABS_TORQUE_SUM], (double)mean_abs_torque);
+    atomicAdd(&A.stats[DRL_STAT_SOLVER_ITERS], (double)cnt.iters);
+    atomicAdd(&A.stats[DRL_STAT_DYN_EVALS], (double)cnt.evals);
+    if (A.extras) {
+      float* ex = A.extras + (size_t)env * 16;
+      ex[0] = pos_rew; ex[1] = vel_rew; ex[2] = com_rew; ex[3] = walked; ex[4] = mean_abs_torque;
+      ex[5] = des0; ex[6] = phase0; ex[7] = zoff;
+    }
+  }
+  if (done && l == 0 && live) {
+    const int ep_len = bad ? ep_dur_before + 1 : c.ep_dur;
+    float* ms = sf + 3 * G;
+    const int fl = c.flags;
+    auto smooth = [&](int slot, int bit, float nv, float f) {
+      ms[slot] = (fl >> bit) & 1 ? f * nv + (1.f - f) * ms[slot] : nv;   // utils.py:312-329
+    };
+    if (ep_len > 1) { smooth(kMiscMeanRewSm, 0, ep_ret / (float)(ep_len - 1), 0.9f); c.flags |= 1; }
+    smooth(kMiscPosSm, 1, (float)(sd[0] / sd[3]), 0.9f);
+    smooth(kMiscVelSm, 1, (float)(sd[1] / sd[3]), 0.9f);
+    smooth(kMiscComSm, 1, (float)(sd[2] / sd[3]), 0.9f);
+    smooth(kMiscEpRetSm, 1, ep_ret, 0.25f);
+    smooth(kMiscEpLenSm, 1, (float)ep_len, 0.75f);
+    smooth(kMiscTorSm, 1, ep_tor / (float)ep_len, 0.75f);
+    c.flags |= 2;
+    ms[kMiscMoved] = walked;
+    atomicAdd(&A.stats[DRL_STAT_EPISODES], 1.0);
+    atomicAdd(&A.stats[DRL_STAT_EP_LEN_SUM], (double)ep_len);
+    atomicAdd(&A.stats[DRL_STAT_EP_RET_SUM], (double)ep_ret);
+    if (ep_len > 1) atomicAdd(&A.stats[DRL_STAT_EP_MEAN_REW_SUM], (double)(ep_ret / (float)(ep_len - 1)));
+    atomicAdd(&A.stats[DRL_STAT_MOVED_DISTANCE_SUM], (double)walked);
+    atomicAdd(&A.stats[bad ? DRL_STAT_BLOWUPS : (timeout ? DRL_STAT_TIMEOUTS : DRL_STAT_FALLS)], 1.0);
+    if (A.ring_cap > 0) {
+      const unsigned long long slot = atomicAdd(A.ring_head, 1ull) % (unsigned long long)A.ring_cap;
+      A.ring_len[slot] = ep_len;
+      A.ring_ret[slot] = ep_ret;
+    }
+  }
+  c.flags = __shfl_sync(kFull, c.flags, 0, G);
+  // ---- auto-reset (DummyVecEnv.step_wait), warp-uniform: both environments compute it, only `done` ones commit -----
+  if (__any_sync(kFull, done)) {
+    Cursor c2 = c;
+    float q2 = q, v2 = v, dist2 = dist, zoff2 = zoff;
+    reset_env<G>(M, A, E, L, env, c2, q2, v2, dist2, zoff2);
+    float ph, dv;
+    build_obs<G>(M, A, E, L, c2, q2, v2, ph, dv);
+    const bool left2 = M.mirror_policy && A.left_step[c2.i_step];
+    write_obs<G>(M, E, l, left2, live && done, obs_out);
+    write_obs<G>(M, E, l, left2, live && bad && A.terminal_obs != nullptr,
+                 A.terminal_obs ? A.terminal_obs + (size_t)env * M.obs_dim : obs_out);
+    if (done) {
+      c = c2; q = q2; v = v2; dist = dist2; zoff = zoff2;
+      a = 0.f;
+      walked = 0.f; ep_ret = 0.f; ep_tor = 0.f;
+      pos_rew = vel_rew = com_rew = 1.f;      // get_imitation_reward() inside reset_model (mimic_env.py:562)
+    }
+  }
+  // ---- store -------------------------------------------------------------------------------------------------------
+  if (live) {
+    sf[l] = q; sf[G + l] = v; sf[2 * G + l] = a;
+    if (l == 0) {
+      A.rew[env] = reward;
+      A.done[env] = done ? 1 : 0;
+      float* ms = sf + 3 * G;
+      ms[kMiscDist] = dist; ms[kMiscZoff] = zoff; ms[kMiscWalked] = walked; ms[kMiscEpRet] = ep_ret;
+      ms[kMiscEpTor] = ep_tor; ms[kMiscPrevPos] = pos_rew; ms[kMiscPrevVel] = vel_rew; ms[kMiscPrevCom] = com_rew;
+      si[kCurIstep] = c.i_step; si[kCurPos] = c.pos; si[kCurCount] = c.count; si[kCurEpDur] = c.ep_dur;
+      si[kCurRsiStep] = c.rsi_step; si[kCurNDet] = c.n_det; si[kCurResets] = c.resets; si[kCurFlags] = c.flags;
+    }
+  }
 }
 
 // gather of the per-env extras (Monitor attributes served through VecEnv.get_attr)
@@ -1070,11 +1123,11 @@ size_t step_smem_bytes(int G, int envs_per_block) {
   return model + (size_t)envs_per_block * (G == 16 ? sizeof(EnvSmem<16>) : sizeof(EnvSmem<32>));
 }
 
-template <int NV, int G, bool DBG>
+template <int NV, int G, bool RK4, bool DBG>
 static cudaError_t launch_one(const StepArgs& a, int reset_only, int block, cudaStream_t st) {
   const int epb = block / G;
   const size_t smem = step_smem_bytes(G, epb);
-  auto kern = mimic_step_kernel<NV, G, DBG>;
+  auto kern = mimic_step_kernel<NV, G, RK4, DBG>;
   static bool attr_done = false;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
@@ -1086,13 +1139,21 @@ static cudaError_t launch_one(const StepArgs& a, int reset_only, int block, cuda
   return cudaGetLastError();
 }
 
-cudaError_t launch_step(const StepArgs& a, int nv, int G, int reset_only, int block, bool debug, cudaStream_t st) {
-  if (nv == 14 && G == 16) return debug ? launch_one<14, 16, true>(a, reset_only, block, st)
-                                        : launch_one<14, 16, false>(a, reset_only, block, st);
-  if (nv == 14 && G == 32) return debug ? launch_one<14, 32, true>(a, reset_only, block, st)
-                                        : launch_one<14, 32, false>(a, reset_only, block, st);
-  if (nv == 19 && G == 32) return debug ? launch_one<19, 32, true>(a, reset_only, block, st)
-                                        : launch_one<19, 32, false>(a, reset_only, block, st);
+// instantiated: walker3d (nv 14, 16 lanes) and walker_165cm_65kg (nv 19, 32 lanes), RK4 and Euler; the dump variant
+// exists for the Euler kernels only (tests evaluate single forward passes with it)
+cudaError_t launch_step(const StepArgs& a, int nv, int G, int rk4, int reset_only, int block, bool debug,
+                        cudaStream_t st) {
+  if (debug && rk4) return cudaErrorInvalidValue;
+  if (nv == 14 && G == 16) {
+    if (rk4) return launch_one<14, 16, true, false>(a, reset_only, block, st);
+    return debug ? launch_one<14, 16, false, true>(a, reset_only, block, st)
+                 : launch_one<14, 16, false, false>(a, reset_only, block, st);
+  }
+  if (nv == 19 && G == 32) {
+    if (rk4) return launch_one<19, 32, true, false>(a, reset_only, block, st);
+    return debug ? launch_one<19, 32, false, true>(a, reset_only, block, st)
+                 : launch_one<19, 32, false, false>(a, reset_only, block, st);
+  }
   return cudaErrorInvalidValue;
 }
 

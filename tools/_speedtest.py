@@ -1,0 +1,8 @@
+import sys; sys.path.insert(0,'/root/repo')
+from tools.gpu_check import speed, rollout, forward_pieces
+forward_pieces()
+rollout(steps=12)
+for blk in (32,64,128):
+    speed(4096, block=blk)
+speed(65536, block=32); speed(65536, block=64)
+speed(4096, integrator="euler")

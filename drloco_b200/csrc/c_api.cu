@@ -214,6 +214,10 @@ extern "C" int drl_upload_model(DrlEnv* e, const DrlWalkerModel* m) {
       }
     }
   d.nbox_cand = nc;
+  for (int x = 0; x < m->n_box; x++) {
+    if (d.box_body_mask & (1u << m->box_body[x])) return fail(DRL_ERR_UNSUPPORTED, "model: at most one box geom per body");
+    d.box_body_mask |= 1u << m->box_body[x];
+  }
   for (int s = 0; s < m->n_sphere; s++, nc++) {
     if (nc >= kMaxCand) return fail(DRL_ERR_INVALID, "model: too many contact candidates");
     d.cand_body[nc] = m->sphere_body[s];

@@ -55,6 +55,7 @@ struct DevModel {
   float ctrl_freq_inv, w_pos, w_vel, w_com, rew_scale, alive_bonus, fall_z;
   int mirror_obs_idx[kMaxObs], mirror_act_idx[kMaxAct];
   float mirror_obs_sign[kMaxObs], mirror_act_sign[kMaxAct];
+  unsigned box_body_mask;            // bodies that carry a box geom (their contact accumulators are segment-written)
   unsigned com_mask;                 // dofs excluded from the pose / velocity reward (COM indices 0,1,2)
   int com_z_dof;
   // ---- mocap ----

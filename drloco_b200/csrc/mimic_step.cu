@@ -450,22 +450,25 @@ __device__ __forceinline__ void forward_dynamics(const DevModel& M, EnvSmem<G>& 
   if (lsg == 0.f) AS.lbit = false;
   else if (!AS.prev_lim) AS.lbit = true;
   const bool sph_any = __any_sync(kFull, cact[1]);
-  const bool constrained = (conmask != 0u) || __any_sync(kFull, lsg != 0.f);
-  const bool seg_any = __any_sync(kFull, cact[0]);
+  const bool any_limit = __any_sync(kFull, lsg != 0.f);
+  const bool constrained = (conmask != 0u) || any_limit;
   float H[NV + 1];
   for (int it = 0; it < kMaxSolverIter; it++) {
-    if (constrained) {
-      cnt.iters++;
-      // zero the accumulators of every body in the union (an environment may have no contact on some of them)
-      for (unsigned mk = conmask; mk; mk &= mk - 1) {
-        const int b = __ffs(mk) - 1;
-        for (int i = l; i < 24; i += G) E.W[b][i] = 0.f;
-        if (l < 8) E.U[b][l] = 0.f;
+    if (constrained) cnt.iters++;
+    if (conmask != 0u) {
+      // Per-body accumulators W (21) / U (6).  Box bodies are written by their 8-lane segment (zeros when the segment
+      // has no active corner), capsule-only bodies are zeroed here and filled below; no atomics anywhere, so the
+      // result does not depend on scheduling.
+      if (sph_any) {
+        for (unsigned mk = conmask & ~M.box_body_mask; mk; mk &= mk - 1) {
+          const int b = __ffs(mk) - 1;
+          for (int i = l; i < 24; i += G) E.W[b][i] = 0.f;
+          if (l < 8) E.U[b][l] = 0.f;
+        }
       }
-      __syncwarp();
 #pragma unroll
       for (int ps = 0; ps < kNPass; ps++) {
-        if (ps == 0 ? !seg_any : !sph_any) continue;
+        if (ps == 1 && !sph_any) continue;
         // wrench-space Hessian of this contact's active pyramid rows: w = (P x d, d), W += D w w^T, U += D aref w
         float wv[28];
 #pragma unroll
@@ -499,7 +502,7 @@ __device__ __forceinline__ void forward_dynamics(const DevModel& M, EnvSmem<G>& 
         }
         if (ps == 0) {
           // pass 0 holds the box corners: the 8 lanes of a segment belong to one box = one body -> butterfly sum,
-          // then the segment adds its body's accumulators (a body may carry a box and a capsule -> atomics)
+          // then the segment stores its body's accumulators
 #pragma unroll
           for (int i = 0; i < 27; i++) {
             float t = wv[i];
@@ -508,24 +511,29 @@ __device__ __forceinline__ void forward_dynamics(const DevModel& M, EnvSmem<G>& 
             t += __shfl_xor_sync(kFull, t, 4);
             wv[i] = t;
           }
-          const unsigned segact = __ballot_sync(kFull, cact[0]);
-          if ((segact >> (wl & ~7)) & 0xFFu) {
+          if (l < M.nbox_cand) {
             const int sl = wl & 7, b = cbody[0];
 #pragma unroll
             for (int i = 0; i < 27; i++) {
               if ((i & 7) == sl) {
-                float* dst = i < 21 ? &E.W[b][i] : &E.U[b][i - 21];
-                if (sph_any) atomicAdd(dst, wv[i]); else *dst = wv[i];
+                if (i < 21) E.W[b][i] = wv[i]; else E.U[b][i - 21] = wv[i];
               }
             }
           }
-        } else if (bt) {
-          float* Wb = E.W[cbody[ps]];
-          float* Ub = E.U[cbody[ps]];
+        } else {
+          // capsule end spheres: rare; added one contact at a time in lane order (deterministic)
+          __syncwarp();
+          for (unsigned sm = __ballot_sync(kFull, bt != 0u); sm; sm &= sm - 1) {
+            if (wl == __ffs(sm) - 1) {
+              float* Wb = E.W[cbody[ps]];
+              float* Ub = E.U[cbody[ps]];
 #pragma unroll
-          for (int i = 0; i < 21; i++) atomicAdd(&Wb[i], wv[i]);
+              for (int i = 0; i < 21; i++) Wb[i] += wv[i];
 #pragma unroll
-          for (int i = 0; i < 6; i++) atomicAdd(&Ub[i], wv[21 + i]);
+              for (int i = 0; i < 6; i++) Ub[i] += wv[21 + i];
+            }
+            __syncwarp();
+          }
         }
       }
       __syncwarp();
@@ -897,7 +905,11 @@ __global__ void __launch_bounds__(128) mimic_step_kernel(const StepArgs A, const
   bool bad = false;      // MuJoCo's mj_checkPos / mj_checkVel: non-finite or huge state -> MujocoException
   float* dbgp = (DBG && A.debug) ? A.debug + (size_t)env * 32 * 40 : nullptr;
   for (int sub = 0; sub < A.frame_skip; sub++) {
-    bad = bad || env_any(L.isdof && (!(fabsf(q) <= 1e10f) || !(fabsf(v) <= 1e10f)), L.emask);
+    {
+      // (collectives must be reached by every lane: no short-circuit around env_any)
+      const bool blown = env_any(L.isdof && (!(fabsf(q) <= 1e10f) || !(fabsf(v) <= 1e10f)), L.emask);
+      bad = bad || blown;
+    }
     if (bad) { q = L.ref; v = 0.f; a = 0.f; }      // park the environment on a harmless state; it resets below
     if (RK4) {
       const float q0 = q, v0 = v;
@@ -945,7 +957,10 @@ __global__ void __launch_bounds__(128) mimic_step_kernel(const StepArgs A, const
       q = fmaf(h, v, q);
     }
   }
-  bad = bad || env_any(L.isdof && (!(fabsf(q) <= 1e10f) || !(fabsf(v) <= 1e10f)), L.emask);
+  {
+    const bool blown = env_any(L.isdof && (!(fabsf(q) <= 1e10f) || !(fabsf(v) <= 1e10f)), L.emask);
+    bad = bad || blown;
+  }
   if (bad) { q = L.ref; v = 0.f; a = 0.f; }
 
   // ---- environment logic (computed for every lane; the blow-up path overrides the outcome) ------------------------

@@ -1,0 +1,369 @@
+"""GPU parity tests: the CUDA path (through the C-ABI, via drloco_b200.vec_env) against the CPU oracle on the same
+seeded inputs.  Bars (BASELINE.json north_star): trajectory indices / phase / done / reset decisions bit-exact; qpos,
+qvel and rewards within 1e-4 relative over a short horizon (fp32 device vs float64 oracle), divergence reported beyond."""
+import os
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from drloco_b200 import cabi  # noqa: E402
+from drloco_b200.config import EnvConfig  # noqa: E402
+from drloco_b200.walkers import make_spec  # noqa: E402
+
+W3D, W165 = "StraightMimicWalker", "MimicWalker165cm65kg"
+REL_TOL = 1e-4          # stated tolerance: |x_gpu - x_oracle|_inf <= REL_TOL * max(1, |x_oracle|_inf) per env
+
+
+def _env(env_id=W3D, n=64, integrator="rk4", seed=5, ep_dur_max=3000, **kw):
+    from drloco_b200.vec_env import B200MimicVecEnv
+    cfg = EnvConfig(env_id=env_id, integrator=integrator, ep_dur_max=ep_dur_max)
+    return B200MimicVecEnv(env_id, num_envs=n, cfg=cfg, seed=seed, **kw)
+
+
+def _oracle(spec, n, integrator="rk4", physics=None):
+    from oracle.env_oracle import OracleVecEnv
+    from oracle.physics import OraclePhysics
+    integ = cabi.INTEGRATOR_RK4 if integrator == "rk4" else cabi.INTEGRATOR_EULER
+    return OracleVecEnv(spec, n, physics or (lambda: OraclePhysics(spec.model, integ)))
+
+
+def _rsi(spec, n, rng):
+    t = spec.mocap
+    istep = rng.integers(0, t.n_steps, n).astype(np.int32)
+    pos = np.array([rng.integers(0, t.step_len[i]) for i in istep], np.int32)
+    return istep, pos
+
+
+def _rel(x, ref):
+    scale = np.maximum(1.0, np.abs(ref).max(axis=-1, keepdims=True))
+    return float((np.abs(x - ref) / scale).max())
+
+
+def _ora_state(ora):
+    q = np.stack([e.env.qpos for e in ora.envs])
+    v = np.stack([e.env.qvel for e in ora.envs])
+    c = np.array([[e.env.refs.i_step, e.env.refs.pos, e.env.refs.count_steps_same_vel, e.env.ep_dur] for e in ora.envs])
+    return q, v, c
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# one dynamics evaluation: mass matrix, bias force, constrained acceleration
+# --------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("env_id", [W3D, W165])
+def test_forward_dynamics_pieces(env_id):
+    from oracle.physics import OraclePhysics
+    n = 48
+    env = _env(env_id, n, integrator="euler")
+    spec = env.spec
+    env.debug_set(frame_skip_override=1, enable_dump=True)
+    m, t = spec.model, spec.mocap
+    nv, nu = m.nv, m.nu
+    rng = np.random.default_rng(0)
+    P = OraclePhysics(m)
+    rows = rng.integers(0, t.n_samples, n)
+    q, v = t.ref[rows, :nv].copy(), t.ref[rows, nv:2 * nv].copy()
+    for i in range(n):
+        q[i, 3:] += 0.1 * rng.standard_normal(nv - 3)
+        q[i, 0] = rng.uniform(-1, 30)                          # far from the origin: O-relative kinematics must not care
+        q[i, 2] -= P.site_xpos(q[i])[:, 2].min() + rng.uniform(-0.004, 0.004)
+        v[i] += 0.3 * rng.standard_normal(nv)
+    q[0, 8 if env_id == W3D else 12] = -0.03 if env_id == W3D else 0.03     # a knee beyond its limit
+    env.reset()
+    cur = np.zeros((n, 4), np.int32)
+    cur[:, 2] = 1
+    env.set_state(q, v, cur)
+    a = rng.uniform(-1, 1, (n, nu)).astype(np.float32)
+    env.step(a)
+    d = env.debug_read()
+    ncon_total = 0
+    for i in range(n):
+        ctrl = (a[i] * np.float32(300)).astype(np.float64)
+        qq, vv = q[i].astype(np.float32).astype(np.float64), v[i].astype(np.float32).astype(np.float64)
+        Mo, co = P.mass_matrix(qq), P.bias(qq, vv)
+        ao, dg = P.forward(qq, vv, ctrl)
+        Mg, cg, ag = d[i, 2:2 + nv, :nv], d[i, 0, :nv], d[i, 2 + nv, :nv]
+        assert np.abs(Mg - Mo).max() <= 2e-6 * np.abs(Mo).max()
+        assert np.abs(cg - co).max() <= 2e-6 * max(1.0, np.abs(co).max())
+        assert np.abs(ag - ao).max() <= 5e-4 * max(1.0, np.abs(ao).max()), (i, dg.ncon)
+        assert int(d[i, 4 + nv, :].sum()) == dg.ncon                      # same contact set
+        ncon_total += dg.ncon
+    assert ncon_total >= n // 2                                            # the sample does exercise contacts
+    env.close()
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# reset (RSI + ground shift) and short-horizon rollouts
+# --------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("env_id,integrator,steps", [(W3D, "rk4", 8), (W3D, "euler", 8), (W165, "rk4", 6)])
+def test_rollout_parity_short_horizon(env_id, integrator, steps):
+    n = 64
+    env = _env(env_id, n, integrator)
+    spec = env.spec
+    ora = _oracle(spec, n, integrator)
+    rng = np.random.default_rng(1)
+    istep, pos = _rsi(spec, n, rng)
+    og, oo = env.reset(inject=(istep, pos)), ora.reset(istep, pos)
+    assert _rel(og, oo) < 2e-5
+    qg, vg, cg = env.get_state()
+    qo, vo, co = _ora_state(ora)
+    np.testing.assert_array_equal(cg, co)                                  # cursor after RSI + next(): bit-exact
+    assert np.abs(qg - qo).max() < 1e-5
+    curve = []
+    for k in range(steps):
+        a = rng.uniform(-1, 1, (n, spec.act_dim)).astype(np.float32)
+        og, rg, dg, _ = env.step(a, inject=(istep, pos))
+        oo, ro, do, _ = ora.step(a, istep, pos)
+        qg, vg, cg = env.get_state()
+        qo, vo, co = _ora_state(ora)
+        np.testing.assert_array_equal(dg, do, err_msg=f"done flags, step {k}")
+        np.testing.assert_array_equal(cg, co, err_msg=f"cursor, step {k}")
+        eq, ev, er = _rel(qg, qo), _rel(vg, vo), float(np.abs(rg - ro).max())
+        curve.append((eq, ev, er))
+        assert eq < REL_TOL and ev < REL_TOL and er < REL_TOL, (k, eq, ev, er)
+        # phase and desired velocity are pure table lookups: bit-exact against float32(oracle)
+        if spec.phase_from_cursor:
+            left = np.array([bool(spec.mocap.left_step[c[0]]) for c in co])
+            np.testing.assert_array_equal(og[:, 0].astype(np.float32), oo[:, 0].astype(np.float32))
+            np.testing.assert_array_equal(og[:, 1].astype(np.float32), oo[:, 1].astype(np.float32))
+            assert left.any() and (~left).any()
+    print(f"{env_id}/{integrator} divergence (rel q, rel v, abs reward) per step:",
+          ["%.1e/%.1e/%.1e" % c for c in curve])
+    env.close()
+
+
+def test_golden_rollout_from_reference_python(golden_dir):
+    """the first steps of the fixture produced by the reference's own MimicWalker3dEnv (tools/gen_golden.py)."""
+    g = np.load(os.path.join(golden_dir, "w3d_rollout.npz"))
+    n = g["actions"].shape[1]
+    env = _env(W3D, n)
+    env.reset(inject=(g["rsi"][0, :, 0], g["rsi"][0, :, 1]))
+    cur = g["cursor0"].copy()
+    env.set_state(g["qpos0"], g["qvel0"], cur)                  # includes count_steps_same_vel after the construction step (Q14)
+    for t in range(6):
+        obs, rew, done, _ = env.step(g["actions"][t])
+        qg, vg, cg = env.get_state()
+        np.testing.assert_array_equal(done, g["done"][t].astype(bool))
+        np.testing.assert_array_equal(cg, g["cursor"][t])
+        assert _rel(qg, g["qpos"][t]) < REL_TOL and _rel(vg, g["qvel"][t]) < REL_TOL
+        assert np.abs(rew - g["rew"][t]).max() < REL_TOL
+        assert _rel(obs, g["obs"][t]) < REL_TOL
+        ex = env.extras().cpu().numpy()
+        assert np.abs(ex[:, :3] - g["comps"][t]).max() < REL_TOL          # pos / vel / com reward components
+        assert np.abs(ex[:, 3] - g["walked"][t]).max() < 1e-5
+    env.close()
+
+
+def test_long_horizon_divergence_is_reported():
+    """beyond the short horizon fp32 and fp64 trajectories separate at contact events; termination decisions must
+    still agree for as long as the states do."""
+    n, steps = 64, 40
+    env = _env(W3D, n)
+    ora = _oracle(env.spec, n)
+    rng = np.random.default_rng(2)
+    istep, pos = _rsi(env.spec, n, rng)
+    env.reset(inject=(istep, pos))
+    ora.reset(istep, pos)
+    med = []
+    for k in range(steps):
+        a = rng.uniform(-1, 1, (n, 8)).astype(np.float32)
+        _, _, dg, _ = env.step(a, inject=(istep, pos))
+        _, _, do, _ = ora.step(a, istep, pos)
+        qg, _, _ = env.get_state()
+        qo, _, _ = _ora_state(ora)
+        err = np.abs(qg - qo).max(axis=1)
+        med.append(float(np.median(err)))
+        close = err < 1e-3
+        np.testing.assert_array_equal(dg[close], do[close])
+    print("median |q_gpu - q_oracle| per step:", ["%.1e" % x for x in med])
+    assert med[9] < 1e-4 and med[-1] < 1e-2
+    env.close()
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# environment logic on injected states (frame_skip = 0): reward, termination, cursor, Monitor statistics
+# --------------------------------------------------------------------------------------------------------------------
+class _FrozenPhysics:
+    """oracle-side stand-in for 'no physics': states are injected, site positions come from the real kinematics."""
+
+    def __init__(self, model):
+        from oracle.physics import OraclePhysics
+        self._p = OraclePhysics(model)
+        self.qacc_warm = self._p.qacc_warm
+
+    def step(self, q, v, ctrl, nsub):
+        return False
+
+    def site_xpos(self, q):
+        return self._p.site_xpos(q)
+
+
+def test_env_logic_and_monitor_on_injected_states():
+    n, steps = 32, 60
+    env = _env(W3D, n, ep_dur_max=25)                            # short episodes: time-outs occur naturally (hypers.py:58)
+    spec = env.spec
+    env.debug_set(frame_skip_override=0)
+    ora = _oracle(spec, n, physics=lambda: _FrozenPhysics(spec.model))
+    rng = np.random.default_rng(3)
+    istep, pos = _rsi(spec, n, rng)
+    pos = np.minimum(pos, spec.mocap.step_len[istep] - 1).astype(np.int32)
+    pos[:4] = spec.mocap.step_len[istep[:4]] - 1                 # RSI on the last sample: immediate step transition
+    og, oo = env.reset(inject=(istep, pos)), ora.reset(istep, pos)
+    assert _rel(og, oo) < 2e-5
+    n_done = 0
+    for k in range(steps):
+        # perturb the (frozen) states the same way on both sides; drop a few walkers below the fall height
+        qg, vg, cg = env.get_state()
+        dq = (0.02 * rng.standard_normal(qg.shape)).astype(np.float32)
+        dv = (0.2 * rng.standard_normal(vg.shape)).astype(np.float32)
+        q_new, v_new = qg + dq, vg + dv
+        fall = rng.random(n) < 0.03
+        q_new[fall, 2] = 0.45
+        env.set_state(q_new, v_new, cg)
+        for i, e in enumerate(ora.envs):
+            e.env.qpos[:] = q_new[i].astype(np.float64)
+            e.env.qvel[:] = v_new[i].astype(np.float64)
+        a = rng.uniform(-1.5, 1.5, (n, 8)).astype(np.float32)
+        og, rg, dg, ig = env.step(a, inject=(istep, pos))
+        oo, ro, do, io = ora.step(a, istep, pos)
+        np.testing.assert_array_equal(dg, do)
+        np.testing.assert_array_equal(np.signbit(rg), np.signbit(ro))      # -0.0 on a fall, +0.0 on a time-out (Q1)
+        assert np.abs(rg - ro).max() < 2e-5
+        assert _rel(og, oo) < 2e-5
+        for i in np.nonzero(do)[0]:
+            assert _rel(ig[i]["terminal_observation"][None], io[i]["terminal_observation"][None]) < 2e-5
+        _, _, cg2 = env.get_state()
+        np.testing.assert_array_equal(cg2, _ora_state(ora)[2])
+        n_done += int(do.sum())
+    assert n_done > 20
+    # Monitor attributes served through get_attr (callback.py:106-108,142,162-164)
+    for name in ("ep_len_smoothed", "ep_ret_smoothed", "mean_reward_smoothed", "mean_ep_pos_rew_smoothed",
+                 "mean_ep_vel_rew_smoothed", "mean_ep_com_rew_smoothed", "moved_distance",
+                 "mean_abs_ep_torque_smoothed"):
+        got = np.array(env.get_attr(name))
+        want = np.array([float(getattr(m, name)) for m in ora.envs])
+        np.testing.assert_allclose(got, want, rtol=2e-4, atol=2e-5, err_msg=name)
+    lens_o = sorted(x for m in ora.envs for x in m.ep_lens)
+    assert sorted(env.episode_lengths().tolist()) == lens_o
+    st = env.stats()
+    assert st["episodes"] == n_done and st["falls"] + st["timeouts"] == n_done and st["timeouts"] >= 3
+    assert st["ep_len_sum"] == sum(lens_o)
+    env.set_attr("ep_lens", [])                                  # callback.py:69-70
+    assert len(env.episode_lengths()) == 0
+    env.close()
+
+
+def test_blowup_path_and_eval_mode():
+    n = 16
+    env = _env(W3D, n)
+    env.reset()
+    q, v, c = env.get_state()
+    v[3, 0] = 3e10 * 10                                          # MuJoCo would raise on |qvel| > 1e10 (mimic_env.py:86-91)
+    q[5, 7] = np.nan
+    env.set_state(q, v, c)
+    obs, rew, done, infos = env.step(np.zeros((n, 8), np.float32))
+    assert done[3] and done[5] and rew[3] == 0 and not np.signbit(rew[3])
+    assert np.isfinite(obs).all() and "terminal_observation" in infos[3]
+    assert env.stats()["blowups"] == 2
+    # deterministic initialisation during evaluation (straight_walk_trajecs.py:237-265)
+    env.env_method("activate_evaluation")
+    for k in range(3):
+        env.reset()
+        _, _, c = env.get_state()
+        L = env.spec.mocap.step_len[k]
+        inc = env.spec.mocap.increment
+        assert (c[:, 0] == k).all() and (c[:, 1] == (3 * L) // 4 + inc).all()
+    env.close()
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# VecNormalize kernels
+# --------------------------------------------------------------------------------------------------------------------
+def test_vecnormalize_matches_sb3_semantics():
+    from drloco_b200.vec_env import B200VecNormalize
+    from oracle.env_oracle import RunningMeanStd
+    n = 256
+    env = _env(W3D, n)
+    vn = B200VecNormalize(env)
+    D = env.obs_dim
+    obs_rms, ret_rms, ret = RunningMeanStd(shape=(D,)), RunningMeanStd(shape=()), np.zeros(n)
+    rng = np.random.default_rng(4)
+    o = vn.reset()
+    raw = env.obs.cpu().numpy().astype(np.float64)
+    obs_rms.update(raw)
+    want = np.clip((raw - obs_rms.mean) / np.sqrt(obs_rms.var + 1e-8), -10, 10)
+    assert np.abs(o - want).max() < 1e-4
+    for k in range(12):
+        a = rng.uniform(-1, 1, (n, 8)).astype(np.float32)
+        o, r, d, _ = vn.step(a)
+        raw, rr = env.obs.cpu().numpy().astype(np.float64), env.rew.cpu().numpy().astype(np.float64)
+        obs_rms.update(raw)
+        want_o = np.clip((raw - obs_rms.mean) / np.sqrt(obs_rms.var + 1e-8), -10, 10)
+        ret = ret * 0.99 + rr
+        ret_rms.update(ret)
+        want_r = np.clip(rr / np.sqrt(ret_rms.var + 1e-8), -10, 10)
+        ret[d] = 0
+        assert np.abs(o - want_o).max() < 2e-4 and np.abs(r - want_r).max() < 2e-4
+    np.testing.assert_allclose(vn.obs_rms.mean, obs_rms.mean, rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(vn.obs_rms.var, obs_rms.var, rtol=1e-5)
+    assert abs(vn.ret_rms.var - ret_rms.var) < 1e-5 * ret_rms.var and vn.obs_rms.count == pytest.approx(obs_rms.count)
+    sd = vn.state_dict()
+    vn2 = B200VecNormalize(env)
+    vn2.load_state_dict(sd)
+    np.testing.assert_array_equal(vn2.obs_rms.var, vn.obs_rms.var)
+    env.close()
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# full-size properties (BASELINE.json configs[1]: 4096 envs) — size-independent invariants
+# --------------------------------------------------------------------------------------------------------------------
+def test_full_size_invariants_and_determinism():
+    n, steps = 4096, 30
+    outs = []
+    for block in (128, 32):
+        env = _env(W3D, n, seed=11)
+        env.debug_set(block_threads=block)
+        g = torch.Generator(device="cuda")
+        g.manual_seed(0)
+        acts = torch.rand(steps, n, 8, device="cuda", generator=g) * 3 - 1.5
+        env.reset_tensor()
+        tot_done = 0
+        for k in range(steps):
+            obs, rew, done = env.step_tensor(acts[k])
+            tot_done += int(done.sum())
+        q, v, c = env.get_state()
+        o, r = obs.cpu().numpy(), rew.cpu().numpy()
+        assert np.isfinite(o).all() and np.isfinite(q).all() and np.isfinite(v).all()
+        assert (r >= 0).all() and (r <= 1.2 + 1e-6).all()                 # 0.8 + 0.2 + alive bonus 0.2
+        t = env.spec.mocap
+        assert (c[:, 0] >= 0).all() and (c[:, 0] < t.n_steps).all() and (c[:, 1] < t.step_len[c[:, 0]]).all()
+        assert (o[:, 0] >= 0).all() and (o[:, 0] <= 1).all()              # phase variable (straight:173-177)
+        assert (q[:, 2] >= 0.5 - 1e-6).all()                              # fallen walkers were reset (mimic_env.py:120)
+        st = env.stats()
+        assert st["env_steps"] == n * steps and st["episodes"] == tot_done
+        outs.append((o, r, q, c))
+        env.close()
+    # same seed, different CTA shape: bitwise identical (no atomics or races on the state path)
+    for x, y in zip(outs[0], outs[1]):
+        np.testing.assert_array_equal(x, y)
+
+
+def test_c_abi_call_order_errors():
+    import ctypes as C
+    from drloco_b200 import lib
+    l = lib.load()
+    spec = make_spec()
+    cfg = cabi.DrlConfig()
+    cfg.num_envs, cfg.device, cfg.frame_skip, cfg.obs_dim, cfg.act_dim, cfg.ctrl_freq = 8, 0, 5, 29, 8, 200.0
+    h = C.c_void_p()
+    assert l.drl_create(C.byref(cfg), C.byref(h)) == 0
+    dummy = torch.zeros(8 * 29, device="cuda")
+    p = C.c_void_p(dummy.data_ptr())
+    assert l.drl_step(h, p, p, p, p, None, None, None, None) == -3          # DRL_ERR_STATE: nothing uploaded
+    assert b"uploaded" in l.drl_last_error()
+    cm = cabi.pack_model(spec.model)
+    cm.nv = 15
+    assert l.drl_upload_model(h, C.byref(cm)) == -4                          # DRL_ERR_UNSUPPORTED
+    assert l.drl_destroy(h) == 0

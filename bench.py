@@ -31,7 +31,7 @@ sys.path.insert(0, REPO)
 ENV_ID = "StraightMimicWalker"
 ENVS_PER_GPU = 4096
 ALGO_BYTES_PER_ENV_STEP = 425.0        # SURVEY.md §8d / DESIGN.md
-ALGO_FLOP_PER_ENV_STEP = 0.40e6        # counted fp32 flops of one W3D env-step (20 dynamics evaluations)
+ALGO_FLOP_PER_ENV_STEP = 0.32e6        # 16 kFLOP per dynamics evaluation x 20 evaluations (W3D, RK4)
 
 
 def _peaks():

@@ -17,8 +17,8 @@ size_t step_smem_bytes(int G, int envs_per_block);
 cudaError_t launch_step(const StepArgs& a, int nv, int G, int rk4, int reset_only, int block, bool debug,
                         cudaStream_t st);
 cudaError_t launch_extras(const float* state_f, const float* last, float* out, int n, int G, cudaStream_t st);
-cudaError_t launch_state_copy(float* state_f, int* state_i, float* qpos, float* qvel, int* cursor, int n, int nv, int G,
-                              int to_state, cudaStream_t st);
+cudaError_t launch_state_copy(float* state_f, int* state_i, int* state_as, float* qpos, float* qvel, int* cursor, int n,
+                              int nv, int G, int to_state, cudaStream_t st);
 }  // namespace drl
 
 using namespace drl;
@@ -43,10 +43,11 @@ struct DrlEnv {
   DrlConfig cfg;
   DevModel hm;                 // host copy
   bool have_model = false, have_mocap = false;
-  int G = 16, block = 128, nv = 0;
+  int G = 16, block = 64, nv = 0;
   DevModel* d_model = nullptr;
   float* state_f = nullptr;
   int* state_i = nullptr;
+  int* state_as = nullptr;
   double* state_d = nullptr;
   float* extras_last = nullptr;
   double* stats = nullptr;
@@ -86,7 +87,7 @@ extern "C" int drl_create(const DrlConfig* cfg, DrlEnv** out) {
 extern "C" int drl_destroy(DrlEnv* e) {
   if (!e) return DRL_OK;
   cudaSetDevice(e->cfg.device);
-  void* ptrs[] = {e->d_model, e->state_f, e->state_i, e->state_d, e->extras_last, e->stats, e->ref, e->step_vel,
+  void* ptrs[] = {e->d_model, e->state_f, e->state_i, e->state_as, e->state_d, e->extras_last, e->stats, e->ref, e->step_vel,
                   e->step_last_comx, e->des_vel_prefix, e->step_off, e->step_len, e->left_step, e->ring_len,
                   e->ring_ret, e->ring_head, e->debug};
   for (void* p : ptrs)
@@ -279,13 +280,15 @@ extern "C" int drl_upload_model(DrlEnv* e, const DrlWalkerModel* m) {
   d.seed = c.seed; d.env_id_offset = c.env_id_offset;
   e->nv = m->nv;
   e->G = G;
-  e->block = 128;
+  e->block = 64;
   CUDA_TRY(cudaSetDevice(c.device));
   const size_t N = (size_t)c.num_envs;
   if (!e->d_model) {
     CUDA_TRY(cudaMalloc(&e->d_model, sizeof(DevModel)));
     CUDA_TRY(cudaMalloc(&e->state_f, N * 4 * e->G * sizeof(float)));
     CUDA_TRY(cudaMalloc(&e->state_i, N * kCurCount8 * sizeof(int)));
+    CUDA_TRY(cudaMalloc(&e->state_as, N * e->G * sizeof(int)));
+    CUDA_TRY(cudaMemset(e->state_as, 0, N * e->G * sizeof(int)));
     CUDA_TRY(cudaMalloc(&e->state_d, N * 4 * sizeof(double)));
     CUDA_TRY(cudaMalloc(&e->extras_last, N * 16 * sizeof(float)));
     CUDA_TRY(cudaMalloc(&e->stats, DRL_STATS_COUNT * sizeof(double)));
@@ -372,7 +375,7 @@ static StepArgs make_args(DrlEnv* e) {
   memset(&a, 0, sizeof a);
   a.model = e->d_model; a.num_envs = e->cfg.num_envs;
   a.frame_skip = e->frame_skip_override >= 0 ? e->frame_skip_override : e->cfg.frame_skip;
-  a.state_f = e->state_f; a.state_i = e->state_i; a.state_d = e->state_d;
+  a.state_f = e->state_f; a.state_i = e->state_i; a.state_as = e->state_as; a.state_d = e->state_d;
   a.ref = e->ref; a.step_off = e->step_off; a.step_len = e->step_len; a.left_step = e->left_step;
   a.step_vel = e->step_vel; a.step_last_comx = e->step_last_comx; a.des_vel_prefix = e->des_vel_prefix;
   a.extras = e->extras_last; a.stats = e->stats;
@@ -411,7 +414,7 @@ extern "C" int drl_step(DrlEnv* e, const float* actions, float* obs, float* rew,
 extern "C" int drl_get_state(DrlEnv* e, float* qpos, float* qvel, int32_t* cursor, void* stream) {
   int rc = ready(e, "drl_get_state");
   if (rc) return rc;
-  CUDA_TRY(launch_state_copy(e->state_f, e->state_i, qpos, qvel, cursor, e->cfg.num_envs, e->nv, e->G, 0,
+  CUDA_TRY(launch_state_copy(e->state_f, e->state_i, e->state_as, qpos, qvel, cursor, e->cfg.num_envs, e->nv, e->G, 0,
                              (cudaStream_t)stream));
   return DRL_OK;
 }
@@ -419,7 +422,7 @@ extern "C" int drl_get_state(DrlEnv* e, float* qpos, float* qvel, int32_t* curso
 extern "C" int drl_set_state(DrlEnv* e, const float* qpos, const float* qvel, const int32_t* cursor, void* stream) {
   int rc = ready(e, "drl_set_state");
   if (rc) return rc;
-  CUDA_TRY(launch_state_copy(e->state_f, e->state_i, const_cast<float*>(qpos), const_cast<float*>(qvel),
+  CUDA_TRY(launch_state_copy(e->state_f, e->state_i, e->state_as, const_cast<float*>(qpos), const_cast<float*>(qvel),
                              const_cast<int32_t*>(cursor), e->cfg.num_envs, e->nv, e->G, 1, (cudaStream_t)stream));
   return DRL_OK;
 }

@@ -80,6 +80,7 @@ struct StepArgs {
   // persistent state
   float* state_f;                    // [N][4*G]  q | v | qacc_warm | misc
   int* state_i;                      // [N][8]
+  int* state_as;                     // [N][G] packed active set of each lane's contact candidates / limit row
   double* state_d;                   // [N][4] lifetime sums of pos/vel/com reward + count (monitor_wrapper.py:97-99)
   // mocap tables
   const float* ref;                  // [n_samples][2*G]

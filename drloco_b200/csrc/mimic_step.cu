@@ -150,6 +150,13 @@ __device__ __forceinline__ constexpr int sym6(int i, int j) {
   return (i <= j) ? (i * 6 - (i * (i - 1)) / 2 + (j - i)) : (j * 6 - (j * (j - 1)) / 2 + (i - j));
 }
 
+// reciprocal: hardware approximation + one Newton step (relative error ~1e-7, no IEEE-division slow path)
+__device__ __forceinline__ float fast_rcp(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return fmaf(r, fmaf(-x, r, 1.f), r);
+}
+
 // does predicate p hold on any lane of this lane's environment?
 __device__ __forceinline__ bool env_any(bool p, unsigned emask) { return (__ballot_sync(kFull, p) & emask) != 0u; }
 
@@ -162,7 +169,7 @@ __device__ __forceinline__ float ldl_solve_cols(float (&H)[NV + 1], int l) {
 #pragma unroll
   for (int k = 0; k < NV; k++) {
     const float dk = __shfl_sync(kFull, H[k], k, G);
-    const float inv = 1.f / fmaxf(dk, 1e-30f);
+    const float inv = fast_rcp(fmaxf(dk, 1e-30f));
     const float lck = H[k] * inv;          // lanes c > k: l_ck = H[c][k] / d_k (H is symmetric)
     const bool upd = l > k;
     if (l == k) invd = inv;
@@ -809,7 +816,7 @@ __device__ __noinline__ void reset_env(const DevModel& M, const StepArgs& A, Env
 }
 
 template <int NV, int G, bool RK4, bool DBG>
-__global__ void __launch_bounds__(128) mimic_step_kernel(const StepArgs A, const int do_reset_only) {
+__global__ void __launch_bounds__(128, 4) mimic_step_kernel(const StepArgs A, const int do_reset_only) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   DevModel& M = *reinterpret_cast<DevModel*>(smem_raw);
   constexpr int kModelBytes = (sizeof(DevModel) + 15) / 16 * 16;
@@ -848,7 +855,15 @@ __global__ void __launch_bounds__(128) mimic_step_kernel(const StepArgs A, const
   c.rsi_step = si[kCurRsiStep]; c.n_det = si[kCurNDet]; c.resets = si[kCurResets]; c.flags = si[kCurFlags];
   float dist = sf[3 * G + kMiscDist], zoff = sf[3 * G + kMiscZoff];
   Counters cnt = {0, 0};
-  ActiveSet AS = {{0u, 0u}, 0u, false, false};
+  // active set of the last evaluation of the previous step (bits 0-3 / 4-7: pyramid rows of the two candidates,
+  // 8-9: candidates in contact, 10: limit row active, 11: limit violated)
+  int* sa = A.state_as + (size_t)env * G;
+  ActiveSet AS;
+  {
+    const unsigned pk = (unsigned)sa[l];
+    AS.bits[0] = pk & 0xFu; AS.bits[1] = (pk >> 4) & 0xFu; AS.prev_act = (pk >> 8) & 3u;
+    AS.lbit = (pk >> 10) & 1u; AS.prev_lim = (pk >> 11) & 1u;
+  }
   float* obs_out = A.obs + (size_t)env * M.obs_dim;
 
   if (do_reset_only) {
@@ -1073,6 +1088,7 @@ __global__ void __launch_bounds__(128) mimic_step_kernel(const StepArgs A, const
     if (done) {
       c = c2; q = q2; v = v2; dist = dist2; zoff = zoff2;
       a = 0.f;
+      AS.bits[0] = AS.bits[1] = 0u; AS.prev_act = 0u; AS.lbit = AS.prev_lim = false;
       walked = 0.f; ep_ret = 0.f; ep_tor = 0.f;
       pos_rew = vel_rew = com_rew = 1.f;      // get_imitation_reward() inside reset_model (mimic_env.py:562)
     }
@@ -1080,6 +1096,8 @@ __global__ void __launch_bounds__(128) mimic_step_kernel(const StepArgs A, const
   // ---- store -------------------------------------------------------------------------------------------------------
   if (live) {
     sf[l] = q; sf[G + l] = v; sf[2 * G + l] = a;
+    sa[l] = (int)(AS.bits[0] | (AS.bits[1] << 4) | (AS.prev_act << 8) | ((AS.lbit ? 1u : 0u) << 10) |
+                  ((AS.prev_lim ? 1u : 0u) << 11));
     if (l == 0) {
       A.rew[env] = reward;
       A.done[env] = done ? 1 : 0;
@@ -1107,8 +1125,8 @@ __global__ void extras_kernel(const float* __restrict__ state_f, const float* __
 }
 
 // strided copies between the padded state rows and dense [N][nv] user tensors
-__global__ void state_copy_kernel(float* state_f, int* state_i, float* qpos, float* qvel, int* cursor, int n, int nv,
-                                  int G, int to_state) {
+__global__ void state_copy_kernel(float* state_f, int* state_i, int* state_as, float* qpos, float* qvel, int* cursor,
+                                  int n, int nv, int G, int to_state) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n * G) return;
   const int env = i / G, l = i % G;
@@ -1118,6 +1136,7 @@ __global__ void state_copy_kernel(float* state_f, int* state_i, float* qpos, flo
       if (qpos) sf[l] = qpos[env * nv + l];
       if (qvel) sf[G + l] = qvel[env * nv + l];
       sf[2 * G + l] = 0.f;
+      if (qpos || qvel) state_as[(size_t)env * G + l] = 0;
     } else {
       if (qpos) qpos[env * nv + l] = sf[l];
       if (qvel) qvel[env * nv + l] = sf[G + l];
@@ -1146,6 +1165,9 @@ static cudaError_t launch_one(const StepArgs& a, int reset_only, int block, cuda
   static bool attr_done = false;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return e;
+    // all of the unified L1/shared array as shared memory: residency is bounded by the per-env scratch, not by L1 hits
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return e;
     attr_done = true;
   }
@@ -1178,10 +1200,11 @@ cudaError_t launch_extras(const float* state_f, const float* last, float* out, i
   return cudaGetLastError();
 }
 
-cudaError_t launch_state_copy(float* state_f, int* state_i, float* qpos, float* qvel, int* cursor, int n, int nv, int G,
-                              int to_state, cudaStream_t st) {
+cudaError_t launch_state_copy(float* state_f, int* state_i, int* state_as, float* qpos, float* qvel, int* cursor, int n,
+                              int nv, int G, int to_state, cudaStream_t st) {
   const int total = n * G;
-  state_copy_kernel<<<(total + 255) / 256, 256, 0, st>>>(state_f, state_i, qpos, qvel, cursor, n, nv, G, to_state);
+  state_copy_kernel<<<(total + 255) / 256, 256, 0, st>>>(state_f, state_i, state_as, qpos, qvel, cursor, n, nv, G,
+                                                         to_state);
   return cudaGetLastError();
 }
 

@@ -437,22 +437,45 @@ class B200VecNormalize:
         return self.norm_obs_buf, self.norm_rew_buf, done
 
     # -- SB3 numpy API -----------------------------------------------------------------------------------
+    # float32 arrays are returned (SB3 converts observations to float32 tensors anyway); actions go through a pinned
+    # staging buffer, results come back with one asynchronous copy each and a single stream synchronisation.
+    def _host_buffers(self):
+        if not hasattr(self, "_h"):
+            N, D, A = self.num_envs, self._D, self.venv.act_dim
+            self._h = dict(act=torch.zeros(N, A).pin_memory(), obs=torch.zeros(N, D).pin_memory(),
+                           rew=torch.zeros(N).pin_memory(), done=torch.zeros(N, dtype=torch.uint8).pin_memory(),
+                           tobs=torch.zeros(N, D).pin_memory())
+            self._d_act = torch.zeros(N, A, device=self.device)
+            self._no_info = [{} for _ in range(N)]
+        return self._h
+
     def reset(self, inject=None):
-        return self.reset_tensor(inject).cpu().numpy()
+        h = self._host_buffers()
+        h["obs"].copy_(self.reset_tensor(inject), non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return h["obs"].numpy().copy()
 
     def step_async(self, actions, inject=None):
-        a = torch.as_tensor(np.ascontiguousarray(actions, np.float32), device=self.device)
-        self._out = self.step_tensor(a, inject)
+        h = self._host_buffers()
+        h["act"].numpy()[...] = np.asarray(actions, np.float32).reshape(self.num_envs, -1)
+        self._d_act.copy_(h["act"], non_blocking=True)
+        obs, rew, done = self.step_tensor(self._d_act, inject)
+        h["obs"].copy_(obs, non_blocking=True)
+        h["rew"].copy_(rew, non_blocking=True)
+        h["done"].copy_(done, non_blocking=True)
 
     def step_wait(self):
-        obs, rew, done = self._out
-        done_h = done.cpu().numpy().astype(bool)
-        infos = [{} for _ in range(self.num_envs)]
-        if done_h.any():
-            tobs = self.normalize_obs(self.venv.terminal_obs).cpu().numpy()
-            for i in np.nonzero(done_h)[0]:
-                infos[i]["terminal_observation"] = tobs[i]
-        return obs.cpu().numpy(), rew.cpu().numpy(), done_h, infos
+        h = self._h
+        torch.cuda.current_stream(self.device).synchronize()
+        done = h["done"].numpy().astype(bool)
+        infos = list(self._no_info)
+        if done.any():
+            h["tobs"].copy_(self.normalize_obs(self.venv.terminal_obs), non_blocking=True)
+            torch.cuda.current_stream(self.device).synchronize()
+            tobs = h["tobs"].numpy()
+            for i in np.nonzero(done)[0]:
+                infos[i] = {"terminal_observation": tobs[i].copy()}
+        return h["obs"].numpy().copy(), h["rew"].numpy().copy(), done, infos
 
     def step(self, actions, inject=None):
         self.step_async(actions, inject)

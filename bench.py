@@ -100,9 +100,11 @@ def fp32_peak_tflops(torch) -> float:
     return best
 
 
-def _oracle_worker(args):
-    """env-steps/s of the CPU oracle stack in this process: (n_envs, n_steps, seed) -> (steps, seconds)."""
-    n_envs, n_steps, seed = args
+_WORKER = {}
+
+
+def _oracle_init(n_envs, seed_base):
+    """per-process initialiser: one OracleVecEnv per worker, kept across bench steps (like a SubprocVecEnv worker)."""
     import random
 
     import numpy as np
@@ -110,18 +112,31 @@ def _oracle_worker(args):
     from drloco_b200.walkers import make_spec
     from oracle.env_oracle import OracleVecEnv
     from oracle.physics import OraclePhysics
-    spec = make_spec()
+    seed = seed_base + os.getpid()
     random.seed(seed)
-    np.random.seed(seed)
-    rng = np.random.default_rng(seed)
+    np.random.seed(seed % (2 ** 31))
+    spec = make_spec()
     venv = OracleVecEnv(spec, n_envs, lambda: OraclePhysics(spec.model))
     venv.reset()
-    for _ in range(5):
-        venv.step(rng.uniform(-1, 1, (n_envs, spec.act_dim)).astype(np.float32))
+    _WORKER.update(venv=venv, rng=np.random.default_rng(seed), n=n_envs, act=spec.act_dim)
+
+
+def _oracle_run(n_steps):
+    """n_steps control steps of this worker's envs -> (env-steps, seconds)."""
+    import numpy as np
+    w = _WORKER
     t0 = time.perf_counter()
     for _ in range(n_steps):
-        venv.step(rng.uniform(-1, 1, (n_envs, spec.act_dim)).astype(np.float32))
-    return n_envs * n_steps, time.perf_counter() - t0
+        w["venv"].step(w["rng"].uniform(-1, 1, (w["n"], w["act"])).astype(np.float32))
+    return w["n"] * n_steps, time.perf_counter() - t0
+
+
+def _oracle_worker(args):
+    """env-steps/s of the CPU oracle stack in this process: (n_envs, n_steps, seed) -> (steps, seconds)."""
+    n_envs, n_steps, seed = args
+    _oracle_init(n_envs, seed)
+    _oracle_run(5)
+    return _oracle_run(n_steps)
 
 
 def cpu_baseline_single(budget_s: float = 12.0):
@@ -151,12 +166,12 @@ def run_reference(args):
     ctrl_per_step = 40
     ctx = mp.get_context("fork")
     total_steps, t_total = 0, 0.0
-    with ctx.Pool(cores) as pool:
+    with ctx.Pool(cores, initializer=_oracle_init, initargs=(per_proc_envs, 1000)) as pool:
         for k in range(args.warmup):
-            pool.map(_oracle_worker, [(per_proc_envs, 5, 100 + k * cores + c) for c in range(cores)])
+            pool.map(_oracle_run, [5] * cores, chunksize=1)
         t0 = time.perf_counter()
         for k in range(args.steps):
-            res = pool.map(_oracle_worker, [(per_proc_envs, ctrl_per_step, k * cores + c) for c in range(cores)])
+            res = pool.map(_oracle_run, [ctrl_per_step] * cores, chunksize=1)
             total_steps += sum(r[0] for r in res)
         t_total = time.perf_counter() - t0
     value = total_steps / t_total

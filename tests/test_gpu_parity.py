@@ -367,3 +367,52 @@ def test_c_abi_call_order_errors():
     cm.nv = 15
     assert l.drl_upload_model(h, C.byref(cm)) == -4                          # DRL_ERR_UNSUPPORTED
     assert l.drl_destroy(h) == 0
+
+
+def test_odd_env_count_and_masked_reset():
+    """N = 7: the last warp carries one live and one padding environment; masked reset touches only the chosen envs."""
+    n = 7
+    env = _env(W3D, n)
+    ora = _oracle(env.spec, n)
+    rng = np.random.default_rng(6)
+    istep, pos = _rsi(env.spec, n, rng)
+    og, oo = env.reset(inject=(istep, pos)), ora.reset(istep, pos)
+    assert _rel(og, oo) < 2e-5
+    for k in range(4):
+        a = rng.uniform(-1, 1, (n, 8)).astype(np.float32)
+        og, rg, dg, _ = env.step(a, inject=(istep, pos))
+        oo, ro, do, _ = ora.step(a, istep, pos)
+        np.testing.assert_array_equal(dg, do)
+        assert _rel(og, oo) < REL_TOL and np.abs(rg - ro).max() < REL_TOL
+    q0, v0, c0 = env.get_state()
+    mask = torch.tensor([0, 1, 0, 0, 1, 0, 1], dtype=torch.uint8, device="cuda")
+    env.reset_tensor(mask, inject=(istep, pos))
+    q1, v1, c1 = env.get_state()
+    keep = ~mask.cpu().numpy().astype(bool)
+    np.testing.assert_array_equal(q1[keep], q0[keep])
+    np.testing.assert_array_equal(c1[keep], c0[keep])
+    assert (c1[~keep, 3] == 0).all() and (np.abs(q1[~keep] - q0[~keep]).max(axis=1) > 0).all()
+    env.close()
+
+
+def test_w165_config4_invariants():
+    """BASELINE.json configs[3]: MimicWalker165cm65kg on the (synthetic) loco3d mocap, RSI + termination, 16384 envs."""
+    n, steps = 16384, 12
+    env = _env(W165, n, seed=3)
+    assert (env.obs_dim, env.act_dim) == (47, 13) and env.launch_info()["lanes_per_env"] == 32
+    g = torch.Generator(device="cuda")
+    g.manual_seed(1)
+    env.reset_tensor()
+    done_total = 0
+    for k in range(steps):
+        obs, rew, done = env.step_tensor(torch.rand(n, 13, device="cuda", generator=g) * 2 - 1)
+        done_total += int(done.sum())
+    o, r = obs.cpu().numpy(), rew.cpu().numpy()
+    q, v, c = env.get_state()
+    assert np.isfinite(o).all() and np.isfinite(q).all() and (r >= 0).all() and (r <= 1.2 + 1e-6).all()
+    assert (c[:, 0] == 0).all() and (c[:, 1] >= 0).all() and (c[:, 1] < env.spec.mocap.step_len[0] - 1).all()
+    assert (c[:, 1] % env.spec.mocap.increment == 0).sum() >= 0          # base:95-103 advances by 5 samples
+    assert (np.abs(o[:, 0:8:2]) <= 1 + 1e-6).all()                         # phase angles / pi (mimic_env.py:350-352)
+    st = env.stats()
+    assert st["env_steps"] == n * steps and st["episodes"] == done_total
+    env.close()

@@ -166,6 +166,7 @@ extern "C" int drl_upload_model(DrlEnv* e, const DrlWalkerModel* m) {
     d.body_ndof[b]++;
     d.dof_body[j] = b; d.dof_type[j] = m->dof_type[j]; d.dof_axis[j] = m->dof_axis_idx[j];
     d.dof_limited[j] = m->dof_limited[j];
+    d.dof_code[j] = m->dof_axis_idx[j] | (m->dof_axis_sign[j] < 0 ? 4 : 0);
     d.dof_sign[j] = (float)m->dof_axis_sign[j]; d.dof_ref[j] = (float)m->dof_ref[j];
     d.dof_damping[j] = (float)m->dof_damping[j]; d.dof_armature[j] = (float)m->dof_armature[j];
     d.dof_lo[j] = (float)m->dof_range[j][0]; d.dof_hi[j] = (float)m->dof_range[j][1];
@@ -179,8 +180,10 @@ extern "C" int drl_upload_model(DrlEnv* e, const DrlWalkerModel* m) {
       seen_hinge_root = true;
     }
   }
-  for (int b = 0; b < m->nb; b++)
+  for (int b = 0; b < m->nb; b++) {
     if (d.body_ndof[b] == 0) return fail(DRL_ERR_UNSUPPORTED, "model: every body needs at least one joint");
+    d.body_hinge0[b] = d.body_dof0[b] + (b == 0 ? d.nslide : 0);
+  }
   for (int j = 0; j < m->nv; j++) {
     const int b = m->dof_body[j];
     d.dof_last[j] = (j == d.body_dof0[b] + d.body_ndof[b] - 1) ? 1 : 0;

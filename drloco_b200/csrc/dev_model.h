@@ -24,7 +24,7 @@ struct DevModel {
   float root_z0;                     // body_pos[root].z
   // bodies
   int body_parent[kMaxBody];
-  int body_dof0[kMaxBody], body_ndof[kMaxBody];
+  int body_dof0[kMaxBody], body_ndof[kMaxBody], body_hinge0[kMaxBody];   // hinge0: first hinge dof of the body
   unsigned body_supp[kMaxBody];      // dofs that move body b
   unsigned body_sub[kMaxBody];       // bodies in the subtree rooted at b (including b)
   float body_pos[kMaxBody][3], body_ipos[kMaxBody][3], body_inertia[kMaxBody][3];
@@ -32,6 +32,7 @@ struct DevModel {
   int level_count[kMaxLevel], level_body[kMaxLevel][kMaxBody];
   // dofs
   int dof_body[kMaxDof], dof_type[kMaxDof], dof_axis[kMaxDof], dof_limited[kMaxDof], dof_last[kMaxDof];
+  int dof_code[kMaxDof];             // axis index | (axis sign < 0) << 2
   unsigned dof_anc[kMaxDof];         // dofs strictly before j on j's chain
   unsigned dof_desc[kMaxDof];        // dofs r > j with j in anc(r)
   unsigned dof_subbodies[kMaxDof];   // = body_sub[dof_body[j]]

@@ -41,7 +41,7 @@ struct EnvSmem {
   float v[G];               // qvel at the current stage
   float acc[G];             // qacc iterate
   float tau[G];             // actuator force per dof
-  float sn[G], cs[G];       // sin/cos of hinge angles (slides: displacement in sn)
+  float cssn[G][2];         // cos, sin of hinge angles (slides: -, displacement)
   float axw[G][4];          // joint axes in world orientation
   float S[G][8];            // motion vectors (omega, v_O)
   float Fd[G][8];           // bias-acceleration terms during RNE, then Ic * S
@@ -205,17 +205,18 @@ __device__ __forceinline__ void tree_kinematics(const DevModel& M, EnvSmem<G>& E
         R0 = E.bodyR[p][3 * r]; R1 = E.bodyR[p][3 * r + 1]; R2 = E.bodyR[p][3 * r + 2];
         pr = E.bodyR[p][9 + r] + R0 * M.body_pos[b][0] + R1 * M.body_pos[b][1] + R2 * M.body_pos[b][2];
       }
-      const int j0 = M.body_dof0[b], nj = M.body_ndof[b];
-      for (int j = j0; j < j0 + nj; j++) {
-        const int k = M.dof_axis[j];
+      // hinges only: the root slides translate O itself and their world axes are constants (see forward_dynamics)
+      const int j0 = M.body_hinge0[b], j1 = M.body_dof0[b] + M.body_ndof[b];
+      for (int j = j0; j < j1; j++) {
+        const int code = M.dof_code[j];                 // axis index | negative-axis flag << 2
+        const int k = code & 3;
         const float ax = k == 0 ? R0 : (k == 1 ? R1 : R2);
-        E.axw[j][r] = M.dof_sign[j] * ax;
-        if (M.dof_type[j] == 1) {
-          const float c = E.cs[j], s = E.sn[j];
-          if (k == 0) { float u = R1, w = R2; R1 = c * u + s * w; R2 = c * w - s * u; }
-          else if (k == 1) { float u = R2, w = R0; R2 = c * u + s * w; R0 = c * w - s * u; }
-          else { float u = R0, w = R1; R0 = c * u + s * w; R1 = c * w - s * u; }
-        }
+        E.axw[j][r] = (code & 4) ? -ax : ax;
+        const float2 cs = *reinterpret_cast<const float2*>(&E.cssn[j][0]);
+        const float c = cs.x, sn = cs.y;
+        if (k == 0) { float u = R1, w = R2; R1 = c * u + sn * w; R2 = c * w - sn * u; }
+        else if (k == 1) { float u = R2, w = R0; R2 = c * u + sn * w; R0 = c * w - sn * u; }
+        else { float u = R0, w = R1; R0 = c * u + sn * w; R1 = c * w - sn * u; }
       }
       E.bodyR[b][3 * r] = R0; E.bodyR[b][3 * r + 1] = R1; E.bodyR[b][3 * r + 2] = R2;
       E.bodyR[b][9 + r] = pr;
@@ -235,23 +236,25 @@ __device__ __forceinline__ void forward_dynamics(const DevModel& M, EnvSmem<G>& 
   {
     float s = q - L.ref, c = 1.f;
     if (L.isdof && L.type == 1) sincosf(L.sign * (q - L.ref), &s, &c);
-    if (L.isdof) { E.sn[l] = s; E.cs[l] = c; E.v[l] = v; }
+    if (L.isdof) { *reinterpret_cast<float2*>(&E.cssn[l][0]) = make_float2(c, s); E.v[l] = v; }
   }
   __syncwarp();
   float zO = M.root_z0;
-  for (int j = 0; j < M.nslide; j++) zO = fmaf(M.dof_slide_z[j], E.sn[j], zO);
+  for (int j = 0; j < M.nslide; j++) zO = fmaf(M.dof_slide_z[j], E.cssn[j][1], zO);
   // ---- 2. body frames ----------------------------------------------------------------------------
   tree_kinematics<G>(M, E, l);
   // ---- 3. motion vectors, body inertias about O ------------------------------------------------------
   Vec6 S = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   if (L.isdof) {
-    const float ax = E.axw[l][0], ay = E.axw[l][1], az = E.axw[l][2];
     if (L.type == 1) {
+      const float ax = E.axw[l][0], ay = E.axw[l][1], az = E.axw[l][2];
       const float px = E.bodyR[L.body][9], py = E.bodyR[L.body][10], pz = E.bodyR[L.body][11];
       S.w0 = ax; S.w1 = ay; S.w2 = az;
       cross3(S.v0, S.v1, S.v2, px, py, pz, ax, ay, az);     // v_O = anchor x axis
-    } else {
-      S.v0 = ax; S.v1 = ay; S.v2 = az;
+    } else {                                                // root slide: constant world axis +-e_k
+      const int k = M.dof_code[l] & 3;
+      const float sg = (M.dof_code[l] & 4) ? -1.f : 1.f;
+      S.v0 = k == 0 ? sg : 0.f; S.v1 = k == 1 ? sg : 0.f; S.v2 = k == 2 ? sg : 0.f;
     }
     st6(E.S[l], S);
   }
@@ -797,11 +800,11 @@ __device__ __noinline__ void reset_env(const DevModel& M, const StepArgs& A, Env
   {
     float s = q - L.ref, cc = 1.f;
     if (L.isdof && L.type == 1) sincosf(L.sign * (q - L.ref), &s, &cc);
-    if (L.isdof) { E.sn[l] = s; E.cs[l] = cc; }
+    if (L.isdof) *reinterpret_cast<float2*>(&E.cssn[l][0]) = make_float2(cc, s);
   }
   __syncwarp();
   float zO = M.root_z0;
-  for (int j = 0; j < M.nslide; j++) zO = fmaf(M.dof_slide_z[j], E.sn[j], zO);
+  for (int j = 0; j < M.nslide; j++) zO = fmaf(M.dof_slide_z[j], E.cssn[j][1], zO);
   tree_kinematics<G>(M, E, l);
   float sz = 3.0e38f;
   for (int s = l; s < M.nsite; s += G) {

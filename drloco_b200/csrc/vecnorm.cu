@@ -156,3 +156,44 @@ extern "C" int drl_vecnorm_apply(const float* obs_in, float* obs_out, const floa
       (flags >> 1) & 1, (flags >> 2) & 1);
   return cudaGetLastError() == cudaSuccess ? DRL_OK : DRL_ERR_CUDA;
 }
+
+// ---- FP32 roofline denominator: sustained FFMA rate of the device, measured (bench.py "fp32.peak") ----
+namespace drl {
+__global__ void __launch_bounds__(256) ffma_probe_kernel(float* out, int iters, float a, float b) {
+  float x0 = threadIdx.x * 1e-3f, x1 = x0 + 1.f, x2 = x0 + 2.f, x3 = x0 + 3.f;
+  float x4 = x0 + 4.f, x5 = x0 + 5.f, x6 = x0 + 6.f, x7 = x0 + 7.f;
+#pragma unroll 4
+  for (int i = 0; i < iters; i++) {     // 8 independent chains per thread: issue-bound, not latency-bound
+    x0 = fmaf(x0, a, b); x1 = fmaf(x1, a, b); x2 = fmaf(x2, a, b); x3 = fmaf(x3, a, b);
+    x4 = fmaf(x4, a, b); x5 = fmaf(x5, a, b); x6 = fmaf(x6, a, b); x7 = fmaf(x7, a, b);
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+}
+}  // namespace drl
+
+extern "C" int drl_fp32_peak_probe(int32_t device, double* tflops_out) {
+  if (!tflops_out) return DRL_ERR_INVALID;
+  if (cudaSetDevice(device) != cudaSuccess) return DRL_ERR_CUDA;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return DRL_ERR_CUDA;
+  const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 1 << 16;
+  float* buf = nullptr;
+  if (cudaMalloc(&buf, (size_t)blocks * threads * sizeof(float)) != cudaSuccess) return DRL_ERR_CUDA;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  double best = 0.0;
+  for (int rep = 0; rep < 4; rep++) {
+    cudaEventRecord(e0);
+    drl::ffma_probe_kernel<<<blocks, threads>>>(buf, iters, 0.999f, 1e-3f);
+    cudaEventRecord(e1);
+    if (cudaEventSynchronize(e1) != cudaSuccess) { cudaFree(buf); return DRL_ERR_CUDA; }
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    const double flops = 2.0 * 8.0 * (double)iters * blocks * threads;
+    if (rep > 0 && ms > 0.f) best = fmax(best, flops / (ms * 1e-3) / 1e12);
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaFree(buf);
+  *tflops_out = best;
+  return DRL_OK;
+}

@@ -213,6 +213,10 @@ int drl_vecnorm_apply(const float* obs_in, float* obs_out, const float* rew_in, 
                       const double* packed, const double* rms_in, double* rms_out, float* ret, const uint8_t* done,
                       float clip_obs, float clip_rew, float eps, int32_t flags, void* stream);
 
+/* measured sustained FFMA rate of `device` in TFLOP/s (8 independent FMA chains per thread, all SMs): the FP32
+ * roofline denominator bench.py reports next to the HBM one. Synchronises the device. */
+int drl_fp32_peak_probe(int32_t device, double* tflops_out);
+
 /* introspection for benchmarks */
 int drl_launch_info(DrlEnv* env, int32_t* lanes_per_env, int32_t* block_threads, int32_t* grid_blocks,
                     int32_t* smem_bytes);

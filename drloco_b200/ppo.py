@@ -1,0 +1,175 @@
+"""PPO consumer of the GPU rollouts — SURVEY.md §8f "next" row 1 (beyond the hot-path scope; kept deliberately small).
+
+Restates what reference ``drloco/train.py:77-139`` asks Stable-Baselines3 1.0 to do, with the reference's
+hyper-parameters (``drloco/config/hypers.py:68-116``) and network (``drloco/custom/policies.py:13-80``: 2 x 512 tanh hidden
+layers *shared* between policy and value head — Q15 —, state-independent log-std initialised at -0.75), on device
+tensors end to end: observations, actions, rewards and the rollout buffer never leave HBM; the environment is stepped
+through ``B200VecNormalize.step_tensor``.  The MLP uses plain PyTorch (cuBLAS GEMMs): it is not part of the hot path.
+"""
+from __future__ import annotations
+
+import dataclasses
+import math
+import time
+from typing import Callable, List, Optional
+
+import torch
+import torch.nn as nn
+
+
+@dataclasses.dataclass
+class PPOConfig:
+    """defaults = reference hypers.py (StraightMimicWalker, 200 Hz)."""
+    gamma: float = 0.995                 # hypers.py:68
+    gae_lambda: float = 0.95             # SB3 default
+    batch_size: int = 4096 * 4           # hypers.py:79 samples per update (n_steps * n_envs)
+    minibatch_size: int = 512 * 4        # hypers.py:78
+    n_epochs: int = 4                    # hypers.py:116
+    lr_start: float = 500e-6             # hypers.py:85-87, linear decay to lr_final
+    lr_final: float = 1e-6
+    clip_range: float = 0.15             # hypers.py:109 (policy and value function, train.py:114-115)
+    ent_coef: float = -0.0075            # hypers.py:113
+    vf_coef: float = 0.5                 # SB3 default
+    max_grad_norm: float = 0.5           # SB3 default
+    init_logstd: float = -0.75           # hypers.py:75
+    hidden: tuple = (512, 512)           # hypers.py:97
+    total_steps: int = int(8e6)          # hypers.py:90
+
+
+class ActorCritic(nn.Module):
+    """CustomActorCriticPolicy (policies.py:54-80): shared tanh trunk, linear action mean, linear value."""
+
+    def __init__(self, obs_dim: int, act_dim: int, hidden=(512, 512), init_logstd=-0.75):
+        super().__init__()
+        layers, d = [], obs_dim
+        for h in hidden:
+            layers += [nn.Linear(d, h), nn.Tanh()]
+            d = h
+        self.trunk = nn.Sequential(*layers)
+        self.action_net = nn.Linear(d, act_dim)
+        self.value_net = nn.Linear(d, 1)
+        self.log_std = nn.Parameter(torch.full((act_dim,), float(init_logstd)))
+        for m in self.trunk:                              # SB3 ortho_init: sqrt(2) trunk, 0.01 policy, 1 value
+            if isinstance(m, nn.Linear):
+                nn.init.orthogonal_(m.weight, math.sqrt(2))
+                nn.init.zeros_(m.bias)
+        nn.init.orthogonal_(self.action_net.weight, 0.01)
+        nn.init.zeros_(self.action_net.bias)
+        nn.init.orthogonal_(self.value_net.weight, 1.0)
+        nn.init.zeros_(self.value_net.bias)
+
+    def forward(self, obs):
+        z = self.trunk(obs)
+        return self.action_net(z), self.value_net(z).squeeze(-1)
+
+    def dist(self, mean):
+        return torch.distributions.Normal(mean, self.log_std.exp().expand_as(mean))
+
+
+class PPO:
+    """On-policy loop: collect n_steps x N transitions on the device, GAE(lambda), clipped surrogate updates."""
+
+    def __init__(self, env, cfg: Optional[PPOConfig] = None, seed: int = 0):
+        self.env, self.cfg = env, cfg or PPOConfig()
+        self.device = env.device
+        torch.manual_seed(seed)
+        venv = env.venv if hasattr(env, "venv") else env
+        self.N, self.D, self.A = venv.num_envs, venv.obs_dim, venv.act_dim
+        self.n_steps = max(1, self.cfg.batch_size // self.N)          # train.py:112
+        self.policy = ActorCritic(self.D, self.A, self.cfg.hidden, self.cfg.init_logstd).to(self.device)
+        self.opt = torch.optim.Adam(self.policy.parameters(), lr=self.cfg.lr_start, eps=1e-5)
+        self.num_timesteps = 0
+        self.log: List[dict] = []
+        dev, T, N = self.device, self.n_steps, self.N
+        self.buf = dict(obs=torch.zeros(T, N, self.D, device=dev), act=torch.zeros(T, N, self.A, device=dev),
+                        logp=torch.zeros(T, N, device=dev), val=torch.zeros(T, N, device=dev),
+                        rew=torch.zeros(T, N, device=dev), done=torch.zeros(T, N, device=dev))
+
+    def _lr(self) -> float:                                            # schedules.py:16-33 LinearDecay
+        frac = min(1.0, self.num_timesteps / max(1, self.cfg.total_steps))
+        return self.cfg.lr_start + frac * (self.cfg.lr_final - self.cfg.lr_start)
+
+    @torch.no_grad()
+    def collect(self, obs):
+        b = self.buf
+        for t in range(self.n_steps):
+            mean, val = self.policy(obs)
+            d = self.policy.dist(mean)
+            act = d.sample()
+            b["obs"][t], b["act"][t], b["val"][t] = obs, act, val
+            b["logp"][t] = d.log_prob(act).sum(-1)
+            # the env clips to [-1, 1] itself (mimic_env.py:181); SB3's clip to the +-300 action space is a no-op
+            nobs, rew, done = self.env.step_tensor(act.contiguous())
+            b["rew"][t], b["done"][t] = rew, done.float()
+            obs = nobs.clone()
+        _, last_val = self.policy(obs)
+        # GAE; SB3 1.0 does not bootstrap from the terminal observation
+        adv = torch.zeros_like(b["rew"])
+        last = torch.zeros(self.N, device=self.device)
+        for t in reversed(range(self.n_steps)):
+            nv = last_val if t == self.n_steps - 1 else b["val"][t + 1]
+            nonterminal = 1.0 - b["done"][t]
+            delta = b["rew"][t] + self.cfg.gamma * nv * nonterminal - b["val"][t]
+            last = delta + self.cfg.gamma * self.cfg.gae_lambda * nonterminal * last
+            adv[t] = last
+        self.num_timesteps += self.n_steps * self.N
+        return obs, adv, adv + b["val"]
+
+    def update(self, adv, ret):
+        cfg, b = self.cfg, self.buf
+        for g in self.opt.param_groups:
+            g["lr"] = self._lr()
+        flat = lambda x: x.reshape(-1, *x.shape[2:])                  # noqa: E731
+        obs, act, logp0, val0, adv, ret = map(flat, (b["obs"], b["act"], b["logp"], b["val"], adv, ret))
+        n = obs.shape[0]
+        stats = []
+        for _ in range(cfg.n_epochs):
+            perm = torch.randperm(n, device=self.device)
+            for s in range(0, n, cfg.minibatch_size):
+                idx = perm[s:s + cfg.minibatch_size]
+                mean, val = self.policy(obs[idx])
+                d = self.policy.dist(mean)
+                logp = d.log_prob(act[idx]).sum(-1)
+                a = adv[idx]
+                a = (a - a.mean()) / (a.std() + 1e-8)
+                ratio = (logp - logp0[idx]).exp()
+                pl = -torch.min(a * ratio, a * ratio.clamp(1 - cfg.clip_range, 1 + cfg.clip_range)).mean()
+                vclip = val0[idx] + (val - val0[idx]).clamp(-cfg.clip_range, cfg.clip_range)     # clip_range_vf
+                vl = ((ret[idx] - vclip) ** 2).mean()
+                ent = d.entropy().sum(-1).mean()
+                loss = pl + cfg.vf_coef * vl - cfg.ent_coef * ent
+                self.opt.zero_grad(set_to_none=True)
+                loss.backward()
+                nn.utils.clip_grad_norm_(self.policy.parameters(), cfg.max_grad_norm)
+                self.opt.step()
+                stats.append((pl.detach(), vl.detach(), ent.detach()))
+        return [torch.stack(x).mean().item() for x in zip(*stats)]
+
+    def learn(self, total_steps: Optional[int] = None, log_every: int = 10,
+              callback: Optional[Callable[["PPO", dict], None]] = None):
+        total = total_steps or self.cfg.total_steps
+        self.cfg.total_steps = total
+        venv = self.env.venv if hasattr(self.env, "venv") else self.env
+        obs = self.env.reset_tensor().clone()
+        it, t0 = 0, time.time()
+        venv.reset_stats()
+        while self.num_timesteps < total:
+            obs, adv, ret = self.collect(obs)
+            pl, vl, ent = self.update(adv, ret)
+            it += 1
+            if it % log_every == 0 or self.num_timesteps >= total:
+                st = venv.stats()
+                venv.reset_stats()
+                row = dict(steps=self.num_timesteps, wall_s=time.time() - t0,
+                           mean_step_reward=(self.env.get_original_reward().mean().item()
+                                             if hasattr(self.env, "get_original_reward") else float("nan")),
+                           mean_ep_len=st["ep_len_sum"] / max(1.0, st["episodes"]),
+                           mean_ep_ret=st["ep_ret_sum"] / max(1.0, st["episodes"]),
+                           moved_distance=st["moved_distance_sum"] / max(1.0, st["episodes"]),
+                           pos_rew=st["pos_rew_sum"] / max(1.0, st["rew_steps"]),
+                           vel_rew=st["vel_rew_sum"] / max(1.0, st["rew_steps"]),
+                           episodes=st["episodes"], policy_loss=pl, value_loss=vl, entropy=ent, lr=self._lr())
+                self.log.append(row)
+                if callback:
+                    callback(self, row)
+        return self

@@ -74,10 +74,12 @@ class B200MimicVecEnv:
         with torch.cuda.device(self.device):
             N, D = self.num_envs, self.obs_dim
             dev = self.device
-            self.obs = torch.zeros(N, D, device=dev)
-            self.rew = torch.zeros(N, device=dev)
-            self.done = torch.zeros(N, dtype=torch.uint8, device=dev)
-            self.terminal_obs = torch.zeros(N, D, device=dev)
+            # two output sets used alternately: a consumer working on step k (e.g. VecNormalize on a side stream)
+            # is never overwritten by step k+1
+            self._outs = [dict(obs=torch.zeros(N, D, device=dev), rew=torch.zeros(N, device=dev),
+                               done=torch.zeros(N, dtype=torch.uint8, device=dev),
+                               terminal_obs=torch.zeros(N, D, device=dev)) for _ in range(2)]
+            self._cur = 0
             self._actions = torch.zeros(N, self.act_dim, device=dev)
             self._extras = torch.zeros(N, cabi.EXTRA_COUNT, device=dev)
             self._stats = torch.zeros(cabi.STATS_COUNT, dtype=torch.float64, device=dev)
@@ -138,6 +140,12 @@ class B200MimicVecEnv:
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
+    # outputs of the most recent reset / step
+    obs = property(lambda self: self._outs[self._cur]["obs"])
+    rew = property(lambda self: self._outs[self._cur]["rew"])
+    done = property(lambda self: self._outs[self._cur]["done"])
+    terminal_obs = property(lambda self: self._outs[self._cur]["terminal_obs"])
+
     def _inject_tensors(self, inject):
         if inject is None:
             return None, None
@@ -156,16 +164,19 @@ class B200MimicVecEnv:
 
     def step_tensor(self, actions: torch.Tensor, inject=None) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
         """actions: float32 CUDA tensor [N, act_dim].  Returns (obs, rew, done) device tensors owned by the env and
-        overwritten by the next step; ``self.terminal_obs`` rows of done envs hold the pre-reset observation."""
+        overwritten two steps later (outputs alternate between two buffer sets); ``self.terminal_obs`` rows of done
+        envs hold the pre-reset observation."""
         if actions.dtype != torch.float32 or not actions.is_cuda or not actions.is_contiguous() \
                 or tuple(actions.shape) != (self.num_envs, self.act_dim):
             raise ValueError("actions must be a contiguous float32 CUDA tensor of shape [num_envs, act_dim]")
         ii, ip = self._inject_tensors(inject)
+        self._cur ^= 1
+        o = self._outs[self._cur]
         with torch.cuda.device(self.device):
-            lib.check(self._lib.drl_step(self._handle, _ptr(actions), _ptr(self.obs), _ptr(self.rew), _ptr(self.done),
-                                         _ptr(self.terminal_obs), _ptr(ii), _ptr(ip), self._stream()), "drl_step")
+            lib.check(self._lib.drl_step(self._handle, _ptr(actions), _ptr(o["obs"]), _ptr(o["rew"]), _ptr(o["done"]),
+                                         _ptr(o["terminal_obs"]), _ptr(ii), _ptr(ip), self._stream()), "drl_step")
         self.launches += 1
-        return self.obs, self.rew, self.done
+        return o["obs"], o["rew"], o["done"]
 
     # ------------------------------------------------------------------ SB3 VecEnv API (numpy)
     def reset(self, inject=None) -> np.ndarray:
@@ -376,8 +387,15 @@ class B200VecNormalize:
         self._cur = 0
         self._packed = torch.zeros(2 * D + 3, dtype=torch.float64, device=dev)
         self.ret = torch.zeros(self.num_envs, device=dev)
-        self.norm_obs_buf = torch.zeros(self.num_envs, D, device=dev)
-        self.norm_rew_buf = torch.zeros(self.num_envs, device=dev)
+        self._nobs = [torch.zeros(self.num_envs, D, device=dev) for _ in range(2)]
+        self._nrew = [torch.zeros(self.num_envs, device=dev) for _ in range(2)]
+        self._k = 0
+        # the statistics / normalisation chain (two kernels + the all-reduce) runs on a side stream so that it can
+        # overlap the next env step when the caller does not consume the normalised tensors immediately
+        with torch.cuda.device(dev):
+            self._side = torch.cuda.Stream(device=dev)
+            self._done_ev = [torch.cuda.Event(), torch.cuda.Event()]
+        self._ev_used = [False, False]
         if distributed is None:
             distributed = torch.distributed.is_available() and torch.distributed.is_initialized() \
                 and torch.distributed.get_world_size() > 1
@@ -390,21 +408,36 @@ class B200VecNormalize:
     # -- SB3 attribute surface ----------------------------------------------------------------------
     @property
     def obs_rms(self):
+        self.synchronize()
         r, D = self._rms[self._cur], self._D
         return RunningMeanStdView(r[:D].cpu().numpy(), r[D:2 * D].cpu().numpy(), float(r[2 * D]))
 
     @property
     def ret_rms(self):
+        self.synchronize()
         r, D = self._rms[self._cur], self._D
         return RunningMeanStdView(float(r[2 * D + 1]), float(r[2 * D + 2]), float(r[2 * D + 3]))
 
     def _flags(self):
         return (1 if self.training else 0) | (2 if self.norm_obs else 0) | (4 if self.norm_reward else 0)
 
-    def _normalize(self, obs, rew, done):
+    norm_obs_buf = property(lambda self: self._nobs[self._k])
+    norm_rew_buf = property(lambda self: self._nrew[self._k])
+
+    def _normalize(self, obs, rew, done, wait=True):
+        """enqueue moments -> (all-reduce) -> apply for the env outputs just produced on the current stream.
+        wait=True makes the current stream wait for the result (normal use); wait=False leaves the chain running on
+        the side stream (``synchronize()`` / the next ``wait=True`` call / a stream sync picks it up)."""
         v = self.venv
-        st = v._stream()
-        with torch.cuda.device(self.device):
+        main = torch.cuda.current_stream(self.device)
+        self._k ^= 1
+        k = self._k
+        nobs, nrew = self._nobs[k], self._nrew[k]
+        ready = torch.cuda.Event()
+        ready.record(main)
+        with torch.cuda.device(self.device), torch.cuda.stream(self._side):
+            self._side.wait_event(ready)
+            st = v._stream()
             packed = None
             if self.training:
                 lib.check(self._lib.drl_vecnorm_moments(_ptr(obs), self.num_envs, self._D, _ptr(rew),
@@ -415,25 +448,43 @@ class B200VecNormalize:
                     torch.distributed.all_reduce(self._packed, op=torch.distributed.ReduceOp.SUM)
                 packed = self._packed
             src, dst = self._rms[self._cur], self._rms[1 - self._cur]
-            lib.check(self._lib.drl_vecnorm_apply(_ptr(obs), _ptr(self.norm_obs_buf), _ptr(rew),
-                                                  _ptr(self.norm_rew_buf) if rew is not None else None,
+            lib.check(self._lib.drl_vecnorm_apply(_ptr(obs), _ptr(nobs), _ptr(rew),
+                                                  _ptr(nrew) if rew is not None else None,
                                                   self.num_envs, self._D, _ptr(packed), _ptr(src), _ptr(dst),
                                                   _ptr(self.ret), _ptr(done), float(self.clip_obs),
                                                   float(self.clip_reward), float(self.epsilon), self._flags(), st),
                       "drl_vecnorm_apply")
             self.launches += 1
             self._cur = 1 - self._cur
+            self._done_ev[k].record(self._side)
+            self._ev_used[k] = True
+        if wait:
+            main.wait_event(self._done_ev[k])
+
+    def _guard_reuse(self):
+        """before the env overwrites the output set it used two steps ago, make sure that step's normalisation is done."""
+        k = self._k ^ 1
+        if self._ev_used[k]:
+            torch.cuda.current_stream(self.device).wait_event(self._done_ev[k])
+
+    def synchronize(self):
+        """make the current stream wait for the most recent normalisation."""
+        if self._ev_used[self._k]:
+            torch.cuda.current_stream(self.device).wait_event(self._done_ev[self._k])
 
     # -- tensor API -----------------------------------------------------------------------------------
     def reset_tensor(self, inject=None):
+        self._guard_reuse()
+        self.synchronize()
         obs = self.venv.reset_tensor(None, inject)
         self.ret.zero_()
         self._normalize(obs, None, None)
         return self.norm_obs_buf
 
-    def step_tensor(self, actions, inject=None):
+    def step_tensor(self, actions, inject=None, wait=True):
+        self._guard_reuse()
         obs, rew, done = self.venv.step_tensor(actions, inject)
-        self._normalize(obs, rew, done)
+        self._normalize(obs, rew, done, wait)
         return self.norm_obs_buf, self.norm_rew_buf, done
 
     # -- SB3 numpy API -----------------------------------------------------------------------------------
@@ -496,6 +547,7 @@ class B200VecNormalize:
 
     # -- save / load: same payload as the reference's pickled VecNormalize statistics (utils.py:183-184, 234-240) -----
     def state_dict(self) -> dict:
+        self.synchronize()
         r, D = self._rms[self._cur].cpu().numpy(), self._D
         return dict(obs_mean=r[:D].copy(), obs_var=r[D:2 * D].copy(), obs_count=float(r[2 * D]),
                     ret_mean=float(r[2 * D + 1]), ret_var=float(r[2 * D + 2]), ret_count=float(r[2 * D + 3]),

@@ -184,6 +184,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--envs-per-gpu", type=int, default=ENVS_PER_GPU)
     ap.add_argument("--integrator", default="rk4", choices=["rk4", "euler"])
+    ap.add_argument("--env-id", default=ENV_ID, choices=["StraightMimicWalker", "MimicWalker165cm65kg"],
+                    help="informational runs of the other BASELINE.json configs; the headline is the default")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -215,8 +217,8 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     n = args.envs_per_gpu
-    cfg = EnvConfig(env_id=ENV_ID, integrator=args.integrator)
-    env = B200MimicVecEnv(ENV_ID, num_envs=n, device=f"cuda:{local}", seed=rank, cfg=cfg, env_id_offset=rank * n)
+    cfg = EnvConfig(env_id=args.env_id, integrator=args.integrator)
+    env = B200MimicVecEnv(args.env_id, num_envs=n, device=f"cuda:{local}", seed=rank, cfg=cfg, env_id_offset=rank * n)
     vn = B200VecNormalize(env, distributed=world > 1)
     dev = env.device
     g = torch.Generator(device=dev)
@@ -295,16 +297,21 @@ def main():
     if rank == 0:
         peaks, which = _peaks()
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-        achieved_gbs = ALGO_BYTES_PER_ENV_STEP * n / (kernel_ms * 1e-3) / 1e9
+        # W165 (informational runs): 597 B; flops scaled from W3D by evaluations (40 vs 20) x (19/14)^2
+        algo_bytes = ALGO_BYTES_PER_ENV_STEP if args.env_id == ENV_ID else 597.0
+        algo_flop = ALGO_FLOP_PER_ENV_STEP if args.env_id == ENV_ID else ALGO_FLOP_PER_ENV_STEP * 2 * (19 / 14) ** 2
+        achieved_gbs = algo_bytes * n / (kernel_ms * 1e-3) / 1e9
         fp32_peak = fp32_peak_tflops(local)
-        achieved_tf = ALGO_FLOP_PER_ENV_STEP * n / (kernel_ms * 1e-3) / 1e12
+        achieved_tf = algo_flop * n / (kernel_ms * 1e-3) / 1e12
         line = {
             "metric": "env-steps/s incl. DeepMimic reward", "value": value, "unit": "env-steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic random actions U(-1,1) on the shipped straight-walking mocap, random-init (RSI) states",
-            "config": {"workload": "MimicWalker3d straight walking, %d batched envs per GPU, random-action step+reward "
-                                   "throughput (BASELINE.json configs[1])" % n,
+            "config": {"workload": ("MimicWalker3d straight walking, %d batched envs per GPU, random-action step+reward "
+                                    "throughput (BASELINE.json configs[1])" % n) if args.env_id == ENV_ID else
+                                   ("MimicWalker165cm65kg on the synthetic loco3d mocap, %d envs per GPU, RSI + early "
+                                    "termination (BASELINE.json configs[3])" % n),
                        "envs_per_gpu": n, "integrator": args.integrator, "frame_skip": env.spec.frame_skip,
                        "parallelism": f"env-sharded x{world}", "l2": "state re-read each step; 192 MB flush before e2e",
                        "lanes_per_env": env.launch_info()["lanes_per_env"]},
@@ -314,11 +321,11 @@ def main():
             "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
                          "frac": achieved_gbs / hbm_peak, "traffic": None, "peak_source": which,
                          "kernel": "mimic_step_kernel", "kernel_ms": kernel_ms,
-                         "note": "latency/FP32-bound by construction: 425 algorithmic bytes per env-step"},
+                         "note": "latency/FP32-bound by construction: %d algorithmic bytes per env-step" % algo_bytes},
             "fp32": {"achieved_tflops": achieved_tf, "peak_tflops": fp32_peak,
                      "frac": achieved_tf / fp32_peak if fp32_peak else None,
                      "peak_source": "FFMA probe kernel (8 independent chains/thread, all SMs) measured in this run; nominal 148 SM x 128 x 2 x 1.965 GHz = 74.4",
-                     "algo_flop_per_env_step": ALGO_FLOP_PER_ENV_STEP},
+                     "algo_flop_per_env_step": algo_flop},
             "episode_stats": {"episodes": stats["episodes"], "mean_ep_len": stats["ep_len_sum"] / max(1.0, stats["episodes"]),
                               "reset_rate_per_env_step": stats["episodes"] / max(1.0, stats["env_steps"]),
                               "solver_iters_per_eval": stats["solver_iters"] / max(1.0, stats["dyn_evals"])},

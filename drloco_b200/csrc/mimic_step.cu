@@ -157,6 +157,16 @@ __device__ __forceinline__ float fast_rcp(float x) {
   return fmaf(r, fmaf(-x, r, 1.f), r);
 }
 
+// pop the two lowest set bits of a mask (i1 = i0 and second = false when only one is left): the chain loops below
+// consume two entries per trip so that their shared-memory loads are in flight together
+__device__ __forceinline__ void pop2(unsigned& mk, int& i0, int& i1, bool& second) {
+  i0 = __ffs(mk) - 1;
+  mk &= mk - 1;
+  second = mk != 0u;
+  i1 = second ? __ffs(mk) - 1 : i0;
+  mk &= mk - 1;
+}
+
 // does predicate p hold on any lane of this lane's environment?
 __device__ __forceinline__ bool env_any(bool p, unsigned emask) { return (__ballot_sync(kFull, p) & emask) != 0u; }
 
@@ -283,9 +293,13 @@ __device__ __forceinline__ void forward_dynamics(const DevModel& M, EnvSmem<G>& 
   // ---- 4. velocities (RNE forward), composite inertias -------------------------------------------------
   if (L.isdof) {
     Vec6 Vp = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    for (unsigned mk = L.anc; mk; mk &= mk - 1) {
-      const int i = __ffs(mk) - 1;
-      axpy6(Vp, E.v[i], ld6(E.S[i]));
+    for (unsigned mk = L.anc; mk;) {
+      int i0, i1; bool two;
+      pop2(mk, i0, i1, two);
+      const Vec6 s0 = ld6(E.S[i0]), s1 = ld6(E.S[i1]);
+      const float v0 = E.v[i0], v1 = two ? E.v[i1] : 0.f;
+      axpy6(Vp, v0, s0);
+      axpy6(Vp, v1, s1);
     }
     // cdof_dot * v = (Vp x_m S) v
     Vec6 cd;
@@ -321,9 +335,12 @@ __device__ __forceinline__ void forward_dynamics(const DevModel& M, EnvSmem<G>& 
   // ---- 5. body forces; contact candidates ---------------------------------------------------------------
   if (L.isbody) {
     Vec6 Ab = {0.f, 0.f, 0.f, 0.f, 0.f, -M.gravity_z};     // fictitious base acceleration = -gravity
-    for (unsigned mk = M.body_supp[l]; mk; mk &= mk - 1) {
-      const int i = __ffs(mk) - 1;
-      axpy6(Ab, 1.f, ld6(E.Fd[i]));
+    for (unsigned mk = M.body_supp[l]; mk;) {
+      int i0, i1; bool two;
+      pop2(mk, i0, i1, two);
+      const Vec6 f0 = ld6(E.Fd[i0]), f1 = ld6(E.Fd[i1]);
+      axpy6(Ab, 1.f, f0);
+      axpy6(Ab, two ? 1.f : 0.f, f1);
     }
     const Vec6 Vb = ld6(E.V[l]);
     Vec6 f = inertia_mul(E.Ib[l], Ab);
@@ -411,9 +428,12 @@ __device__ __forceinline__ void forward_dynamics(const DevModel& M, EnvSmem<G>& 
   Vec6 Fdc = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   if (L.isdof) {
     float cb = 0.f;
-    for (unsigned mk = L.subb; mk; mk &= mk - 1) {
-      const int b = __ffs(mk) - 1;
-      cb += dot6(S, ld6(E.A[b]));
+    for (unsigned mk = L.subb; mk;) {
+      int b0, b1; bool two;
+      pop2(mk, b0, b1, two);
+      const Vec6 f0 = ld6(E.A[b0]), f1 = ld6(E.A[b1]);
+      const float d0 = dot6(S, f0), d1 = dot6(S, f1);
+      cb += d0 + (two ? d1 : 0.f);
     }
     rhs0 = tau - L.damping * v - cb;
     Fdc = inertia_mul(E.Ic[L.body], S);
@@ -595,9 +615,13 @@ __device__ __forceinline__ void forward_dynamics(const DevModel& M, EnvSmem<G>& 
     // ---- re-evaluate the rows at the new qacc: J_i a = w_i . (S_b a) ----
     if (L.isbody && ((conmask >> l) & 1u)) {
       Vec6 Tb = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-      for (unsigned mk = M.body_supp[l]; mk; mk &= mk - 1) {
-        const int i = __ffs(mk) - 1;
-        axpy6(Tb, E.acc[i], ld6(E.S[i]));
+      for (unsigned mk = M.body_supp[l]; mk;) {
+        int i0, i1; bool two;
+        pop2(mk, i0, i1, two);
+        const Vec6 s0 = ld6(E.S[i0]), s1 = ld6(E.S[i1]);
+        const float a0 = E.acc[i0], a1 = two ? E.acc[i1] : 0.f;
+        axpy6(Tb, a0, s0);
+        axpy6(Tb, a1, s1);
       }
       st6(E.T[l], Tb);
     }

@@ -291,7 +291,7 @@ def main():
         if world > 1:
             dist.all_reduce(t2, op=dist.ReduceOp.MAX)
         e2e = {"value": world * n * k2 / (float(t2.item()) * 1e-3), "unit": "env-steps/s",
-               "h2d_bytes_per_step": n * env.act_dim * 4, "d2h_bytes_per_step": n * (env.obs_dim * 4 + 4 + 1),
+               "h2d_bytes_per_step": n * env.act_dim * 4, "d2h_bytes_per_step": n * (2 * env.obs_dim * 4 + 4 + 1),   # obs, terminal obs, reward, done
                "steps": k2}
 
     if rank == 0:
@@ -319,7 +319,9 @@ def main():
             "e2e": e2e,
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": achieved_gbs / hbm_peak, "traffic": None, "peak_source": which,
+                         "frac": achieved_gbs / hbm_peak,
+                         # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full (profiles/r01_step_kernel_final.md)
+                         "traffic": 2450176 if (args.env_id == ENV_ID and n == 4096) else None, "peak_source": which,
                          "kernel": "mimic_step_kernel", "kernel_ms": kernel_ms,
                          "note": "latency/FP32-bound by construction: %d algorithmic bytes per env-step" % algo_bytes},
             "fp32": {"achieved_tflops": achieved_tf, "peak_tflops": fp32_peak,

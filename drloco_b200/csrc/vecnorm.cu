@@ -157,6 +157,36 @@ extern "C" int drl_vecnorm_apply(const float* obs_in, float* obs_out, const floa
   return cudaGetLastError() == cudaSuccess ? DRL_OK : DRL_ERR_CUDA;
 }
 
+// terminal observations of the environments that finished this step, normalised with the current statistics
+// (what VecNormalize hands to SB3 in infos[i]["terminal_observation"]); rows of running environments are skipped
+namespace drl {
+__global__ void vecnorm_terminal_kernel(const float* __restrict__ tin, float* __restrict__ tout,
+                                        const unsigned char* __restrict__ done, int n, int d,
+                                        const double* __restrict__ rms, float clip_obs, float eps, int norm_obs) {
+  const long long total = (long long)n * d;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+       e += (long long)gridDim.x * blockDim.x) {
+    const int row = (int)(e / d), col = (int)(e % d);
+    if (!done[row]) continue;
+    float x = tin[e];
+    if (norm_obs)
+      x = fminf(fmaxf((x - (float)rms[col]) * (float)(1.0 / sqrt(rms[d + col] + (double)eps)), -clip_obs), clip_obs);
+    tout[e] = x;
+  }
+}
+}  // namespace drl
+
+extern "C" int drl_vecnorm_terminal(const float* tobs_in, float* tobs_out, const uint8_t* done, int32_t n, int32_t d,
+                                    const double* rms, float clip_obs, float eps, int32_t norm_obs, void* stream) {
+  if (!tobs_in || !tobs_out || !done || !rms || n <= 0 || d <= 0) return DRL_ERR_INVALID;
+  long long work = (long long)n * d;
+  int blocks = (int)((work + drl::kVnThreads * 4 - 1) / (drl::kVnThreads * 4));
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  drl::vecnorm_terminal_kernel<<<blocks, drl::kVnThreads, 0, (cudaStream_t)stream>>>(tobs_in, tobs_out, done, n, d, rms,
+                                                                                    clip_obs, eps, norm_obs);
+  return cudaGetLastError() == cudaSuccess ? DRL_OK : DRL_ERR_CUDA;
+}
+
 // ---- FP32 roofline denominator: sustained FFMA rate of the device, measured (bench.py "fp32.peak") ----
 namespace drl {
 __global__ void __launch_bounds__(256) ffma_probe_kernel(float* out, int iters, float a, float b) {

@@ -35,6 +35,7 @@ PROTOTYPES = {
     "drl_launch_info": (C.c_int, [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]),
     "drl_debug_set": (C.c_int, [vp, i32, i32, i32]),
     "drl_debug_read": (C.c_int, [vp, vp, i32]),
+    "drl_vecnorm_terminal": (C.c_int, [vp, vp, vp, i32, i32, vp, f32, f32, i32, vp]),
     "drl_fp32_peak_probe": (C.c_int, [i32, C.POINTER(C.c_double)]),
     "drl_vecnorm_moments": (C.c_int, [vp, i32, i32, vp, vp, f32, vp, vp]),
     "drl_vecnorm_apply": (C.c_int, [vp, vp, vp, vp, i32, i32, vp, vp, vp, vp, vp, f32, f32, f32, i32, vp]),

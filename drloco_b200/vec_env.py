@@ -497,6 +497,7 @@ class B200VecNormalize:
                            rew=torch.zeros(N).pin_memory(), done=torch.zeros(N, dtype=torch.uint8).pin_memory(),
                            tobs=torch.zeros(N, D).pin_memory())
             self._d_act = torch.zeros(N, A, device=self.device)
+            self._d_ntobs = torch.zeros(N, D, device=self.device)
             self._no_info = [{} for _ in range(N)]
         return self._h
 
@@ -511,9 +512,16 @@ class B200VecNormalize:
         h["act"].numpy()[...] = np.asarray(actions, np.float32).reshape(self.num_envs, -1)
         self._d_act.copy_(h["act"], non_blocking=True)
         obs, rew, done = self.step_tensor(self._d_act, inject)
+        with torch.cuda.device(self.device):
+            lib.check(self._lib.drl_vecnorm_terminal(_ptr(self.venv.terminal_obs), _ptr(self._d_ntobs), _ptr(done),
+                                                     self.num_envs, self._D, _ptr(self._rms[self._cur]),
+                                                     float(self.clip_obs), float(self.epsilon), int(self.norm_obs),
+                                                     self.venv._stream()), "drl_vecnorm_terminal")
+        self.launches += 1
         h["obs"].copy_(obs, non_blocking=True)
         h["rew"].copy_(rew, non_blocking=True)
         h["done"].copy_(done, non_blocking=True)
+        h["tobs"].copy_(self._d_ntobs, non_blocking=True)
 
     def step_wait(self):
         h = self._h
@@ -521,8 +529,6 @@ class B200VecNormalize:
         done = h["done"].numpy().astype(bool)
         infos = list(self._no_info)
         if done.any():
-            h["tobs"].copy_(self.normalize_obs(self.venv.terminal_obs), non_blocking=True)
-            torch.cuda.current_stream(self.device).synchronize()
             tobs = h["tobs"].numpy()
             for i in np.nonzero(done)[0]:
                 infos[i] = {"terminal_observation": tobs[i].copy()}

@@ -213,6 +213,11 @@ int drl_vecnorm_apply(const float* obs_in, float* obs_out, const float* rew_in, 
                       const double* packed, const double* rms_in, double* rms_out, float* ret, const uint8_t* done,
                       float clip_obs, float clip_rew, float eps, int32_t flags, void* stream);
 
+/* rows of tobs_in whose done byte is set, normalised with rms ({mean[d], var[d], ...}) into tobs_out: the
+ * infos[i]["terminal_observation"] VecNormalize returns (SB3 VecNormalize.step_wait). Other rows are left untouched. */
+int drl_vecnorm_terminal(const float* tobs_in, float* tobs_out, const uint8_t* done, int32_t n, int32_t d,
+                         const double* rms, float clip_obs, float eps, int32_t norm_obs, void* stream);
+
 /* measured sustained FFMA rate of `device` in TFLOP/s (8 independent FMA chains per thread, all SMs): the FP32
  * roofline denominator bench.py reports next to the HBM one. Synchronises the device. */
 int drl_fp32_peak_probe(int32_t device, double* tflops_out);

@@ -309,6 +309,18 @@ def test_vecnormalize_matches_sb3_semantics():
     np.testing.assert_allclose(vn.obs_rms.mean, obs_rms.mean, rtol=1e-6, atol=1e-7)
     np.testing.assert_allclose(vn.obs_rms.var, obs_rms.var, rtol=1e-5)
     assert abs(vn.ret_rms.var - ret_rms.var) < 1e-5 * ret_rms.var and vn.obs_rms.count == pytest.approx(obs_rms.count)
+    # terminal observations come back normalised with the current statistics (SB3 VecNormalize.step_wait)
+    q, v, c = env.get_state()
+    q[:5, 2] = 0.45
+    env.set_state(q, v, c)
+    o, r, d, infos = vn.step(np.zeros((n, 8), np.float32))
+    assert d[:5].all()
+    raw_t = env.terminal_obs.cpu().numpy().astype(np.float64)
+    m, var = vn.obs_rms.mean, vn.obs_rms.var
+    for i in range(5):
+        want_t = np.clip((raw_t[i] - m) / np.sqrt(var + 1e-8), -10, 10)
+        assert np.abs(infos[i]["terminal_observation"] - want_t).max() < 2e-4
+    assert all("terminal_observation" not in infos[i] for i in np.nonzero(~d)[0])
     sd = vn.state_dict()
     vn2 = B200VecNormalize(env)
     vn2.load_state_dict(sd)

@@ -153,8 +153,12 @@ def run_reference(args, emit):
     ctx = mp.get_context("fork")
     total_steps, t_total = 0, 0.0
     with ctx.Pool(cores, initializer=_oracle_init, initargs=(per_proc_envs, 1000)) as pool:
+        t0 = time.perf_counter()
         for k in range(args.warmup):
             pool.map(_oracle_run, [5] * cores, chunksize=1)
+        per_ctrl = (time.perf_counter() - t0) / (5 * args.warmup)       # seconds per control step of all workers
+        # bound the whole timed run to ~2 minutes whatever --steps is
+        ctrl_per_step = max(1, min(ctrl_per_step, int(120.0 / (per_ctrl * max(1, args.steps)))))
         t0 = time.perf_counter()
         for k in range(args.steps):
             res = pool.map(_oracle_run, [ctrl_per_step] * cores, chunksize=1)

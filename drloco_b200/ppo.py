@@ -173,3 +173,53 @@ class PPO:
                 if callback:
                     callback(self, row)
         return self
+
+
+@torch.no_grad()
+def evaluate_walking(policy: ActorCritic, train_env, n_episodes: int = 20, min_stable_distance: float = 15.0):
+    """Deterministic evaluation in the spirit of reference ``TrainingMonitor.eval_walking`` (callback.py:272-390):
+    ``n_episodes`` episodes from the deterministic initial states (step i of the mocap at 75 % of the step,
+    straight_walk_trajecs.py:237-265), deterministic actions, frozen normalisation statistics; reports walked distance,
+    episode duration and the count of stable walks (callback.py:336-349).  The episodes run side by side in one small
+    batched env instead of one after the other."""
+    from .vec_env import B200MimicVecEnv, B200VecNormalize
+    import numpy as np
+    venv = train_env.venv
+    spec = venv.spec
+    t = spec.mocap
+    env = B200MimicVecEnv(spec.cfg.env_id, num_envs=n_episodes, device=venv.device, cfg=spec.cfg, spec=spec, seed=0)
+    vn = B200VecNormalize(env, training=False, norm_reward=False)
+    vn.load_state_dict({**train_env.state_dict(), "norm_reward": False})
+    istep = (np.arange(n_episodes) % t.n_steps).astype(np.int32)
+    pos = ((3 * t.step_len[istep]) // 4).astype(np.int32)
+    obs = vn.reset_tensor(inject=(istep, pos)).clone()
+    n = n_episodes
+    alive = torch.ones(n, dtype=torch.bool, device=venv.device)
+    ep_len = torch.zeros(n, device=venv.device)
+    rew_sum = torch.zeros(n, device=venv.device)
+    dist = torch.zeros(n, device=venv.device)
+    for _ in range(spec.cfg.ep_dur_max + 1):
+        mean, _ = policy(obs)
+        nobs, rew, done = vn.step_tensor(mean.contiguous(), inject=(istep, pos))
+        d = done.bool()
+        ex = env.extras()
+        # walked distance so far (mimic_env.py:295); for an env that just finished, the value at its episode end
+        walked = torch.where(d, ex[:, 14], ex[:, 3])
+        ep_len += alive.float()
+        rew_sum += torch.where(alive & ~d, rew, torch.zeros_like(rew))
+        dist = torch.where(alive, walked, dist)
+        alive &= ~d
+        obs = nobs.clone()
+        if not bool(alive.any()):
+            break
+    env.close()
+    ep_len_h, dist_h = ep_len.cpu().numpy(), dist.cpu().numpy()
+    mean_rew = (rew_sum / torch.clamp(ep_len - 1, min=1)).cpu().numpy()
+    reached = int((dist_h >= min_stable_distance).sum())
+    no_fall = int(((ep_len_h >= spec.cfg.ep_dur_max) & (dist_h >= 0.5 * min_stable_distance)).sum())
+    return dict(mean_walked_distance=float(dist_h.mean()), min_walked_distance=float(dist_h.min()),
+                mean_episode_duration=float(ep_len_h.mean() / spec.cfg.ep_dur_max),
+                min_episode_duration=float(ep_len_h.min()),
+                mean_walking_speed=float((dist_h / (ep_len_h / spec.cfg.ctrl_freq)).mean()),
+                mean_reward_means=float((mean_rew.mean() - spec.cfg.alive_bonus) / spec.cfg.rew_scale),
+                count_stable_walks=max(reached, no_fall), n_episodes=n_episodes)

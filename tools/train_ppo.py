@@ -13,7 +13,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 import torch  # noqa: E402
 
-from drloco_b200.ppo import PPO, PPOConfig  # noqa: E402
+from drloco_b200.ppo import PPO, PPOConfig, evaluate_walking  # noqa: E402
 from drloco_b200.vec_env import vec_env  # noqa: E402
 
 
@@ -40,10 +40,12 @@ def main():
     t0 = time.time()
     agent.learn(args.steps, log_every=5, callback=cb)
     torch.cuda.synchronize()
+    ev = evaluate_walking(agent.policy, env)
+    print("evaluation (deterministic policy, 20 deterministic inits):", json.dumps(ev), flush=True)
     os.makedirs(os.path.dirname(args.out) or ".", exist_ok=True)
     with open(args.out, "w") as f:
         json.dump({"envs": args.envs, "total_steps": agent.num_timesteps, "wall_s": time.time() - t0,
-                   "config": {k: v for k, v in vars(cfg).items()}, "curve": agent.log}, f, indent=1)
+                   "config": {k: v for k, v in vars(cfg).items()}, "curve": agent.log, "evaluation": ev}, f, indent=1)
     print("done: %.1f s, %.2e env-steps/s incl. learning" % (time.time() - t0, agent.num_timesteps / (time.time() - t0)))
 
 

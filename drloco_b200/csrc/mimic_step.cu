@@ -43,8 +43,8 @@ struct EnvSmem {
   float tau[G];             // actuator force per dof
   float cssn[G][2];         // cos, sin of hinge angles (slides: -, displacement)
   float axw[G][4];          // joint axes in world orientation
-  float S[G][8];            // motion vectors (omega, v_O)
-  float Fd[G][8];           // bias-acceleration terms during RNE, then Ic * S
+  float S[G][12];           // motion vectors (omega, v_O); row stride 12 floats: lanes reading different rows hit different banks
+  float Fd[G][12];          // bias-acceleration terms during RNE, then Ic * S (same stride)
   float bodyR[kMaxBody][12];  // rotation (row major) + position relative to O
   float Ib[kMaxBody][12];   // spatial inertia about O: m, h[3], Ixx Ixy Ixz Iyy Iyz Izz
   float Ic[kMaxBody][12];   // composite

@@ -48,11 +48,18 @@ struct EnvSmem {
   float bodyR[kMaxBody][12];  // rotation (row major) + position relative to O
   float Ib[kMaxBody][12];   // spatial inertia about O: m, h[3], Ixx Ixy Ixz Iyy Iyz Izz
   float Ic[kMaxBody][12];   // composite
-  float V[kMaxBody][8];     // spatial velocity
-  float A[kMaxBody][8];     // body force (n, f)
-  float T[kMaxBody][8];     // S_b * qacc
-  float W[kMaxBody][24];    // contact Hessian, 21 unique entries
-  float U[kMaxBody][8];     // contact rhs wrench
+  union {
+    struct {
+      float V[kMaxBody][8];     // spatial velocity
+      float A[kMaxBody][8];     // body force (n, f)
+      float T[kMaxBody][8];     // S_b * qacc
+      float W[kMaxBody][24];    // contact Hessian, 21 unique entries
+      float U[kMaxBody][8];     // contact rhs wrench
+    };
+    // lower triangle of the mass matrix with an odd row stride (transposed without bank conflicts).  Lives between
+    // the last use of V / A (bias force) and the first use of W / U / T (constraint solve).
+    float Mt[kMaxBody * 56];
+  };
   float obsbuf[kMaxObs];
 };
 
@@ -233,6 +240,31 @@ __device__ __forceinline__ void tree_kinematics(const DevModel& M, EnvSmem<G>& E
     }
     __syncwarp();
   }
+}
+
+// Column l of the joint-space inertia matrix.  M[r][c] = S_c . (Ic_{body(r)} S_r) for r = c or a descendant of c (CRBA,
+// E.Fd holds Ic S).  Each lane computes the part of its column at and below the diagonal; the part above comes from
+// the transposed entries through shared memory (odd row stride: the row-wise store and the column-wise load are both
+// conflict-free).  E.Mt aliases V/A/T/W/U: callers guarantee those are dead; ends with a barrier.
+template <int NV, int G>
+__device__ __forceinline__ void mass_column(EnvSmem<G>& E, const LaneConst& L, const Vec6& S, float (&Mcol)[NV]) {
+  constexpr int kMs = (NV % 2 == 0) ? NV + 1 : NV + 2;
+  static_assert(NV * kMs <= (int)(sizeof(E.Mt) / sizeof(float)), "Mt too small");
+  const int l = L.l;
+  const unsigned lowmask = L.isdof ? (L.desc | (1u << l)) : 0u;
+#pragma unroll
+  for (int r = 0; r < NV; r++) {
+    const float d = dot6(S, ld6(E.Fd[r]));
+    Mcol[r] = ((lowmask >> r) & 1u) ? d : 0.f;
+    if (L.isdof) E.Mt[r * kMs + l] = Mcol[r];
+  }
+  __syncwarp();
+#pragma unroll
+  for (int r = 0; r < NV; r++) {
+    if (L.isdof && r < l) Mcol[r] = E.Mt[l * kMs + r];
+    if (r == l) Mcol[r] += L.armature;
+  }
+  __syncwarp();
 }
 
 // One forward-dynamics evaluation (mj_forward).  q, v: this lane's coordinates; a: warm start in, qacc out.
@@ -442,18 +474,11 @@ __device__ __forceinline__ void forward_dynamics(const DevModel& M, EnvSmem<G>& 
   }
   __syncwarp();
   // ---- 7. mass-matrix column ---------------------------------------------------------------------------------
-  // M[r][c] = S_shallow . (Ic_deep S_deep): rows at or below this dof read Fd[r], rows above read S[r]
   float Mcol[NV];
-  const unsigned relmask = L.isdof ? (L.anc | L.desc | (1u << l)) : 0u;
+  mass_column<NV, G>(E, L, S, Mcol);
+  if (DBG) {
 #pragma unroll
-  for (int r = 0; r < NV; r++) {
-    const bool deeper = r >= l;
-    const Vec6 x = ld6(deeper ? E.Fd[r] : E.S[r]);
-    const float d = deeper ? dot6(S, x) : dot6(Fdc, x);
-    float mv = ((relmask >> r) & 1u) ? d : 0.f;
-    if (r == l) mv += L.armature;
-    Mcol[r] = mv;
-    if (DBG) dbg[(2 + r) * 32 + l] = mv;
+    for (int r = 0; r < NV; r++) dbg[(2 + r) * 32 + l] = Mcol[r];
   }
   // ---- joint limits ---------------------------------------------------------------------------------------------
   float lsg = 0.f, lD = 0.f, laref = 0.f;
@@ -978,19 +1003,15 @@ __global__ void __launch_bounds__(128, 4) mimic_step_kernel(const StepArgs A, co
       __syncwarp();   // E.acc holds the constrained qacc of every dof
       float Hc[NV + 1];
       float Ma = 0.f;
-      const Vec6 S = L.isdof ? ld6(E.S[l]) : Vec6{0, 0, 0, 0, 0, 0};
-      const Vec6 Fdc = L.isdof ? ld6(E.Fd[l]) : Vec6{0, 0, 0, 0, 0, 0};
-      const unsigned relmask = L.isdof ? (L.anc | L.desc | (1u << l)) : 0u;
+      {
+        float Mc[NV];
+        const Vec6 S = L.isdof ? ld6(E.S[l]) : Vec6{0, 0, 0, 0, 0, 0};
+        mass_column<NV, G>(E, L, S, Mc);
 #pragma unroll
-      for (int r = 0; r < NV; r++) {
-        const bool deeper = r >= l;
-        const Vec6 x = ld6(deeper ? E.Fd[r] : E.S[r]);
-        const float d = deeper ? dot6(S, x) : dot6(Fdc, x);
-        float mv = ((relmask >> r) & 1u) ? d : 0.f;
-        if (r == l) mv += L.armature;
-        Ma = fmaf(mv, E.acc[r], Ma);
-        if (r == l) mv += h * L.damping;
-        Hc[r] = mv;
+        for (int r = 0; r < NV; r++) {
+          Ma = fmaf(Mc[r], E.acc[r], Ma);
+          Hc[r] = Mc[r] + (r == l ? h * L.damping : 0.f);
+        }
       }
       Hc[NV] = Ma;
       float an = ldl_solve_cols<NV, G>(Hc, l);

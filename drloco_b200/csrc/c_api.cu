@@ -43,7 +43,7 @@ struct DrlEnv {
   DrlConfig cfg;
   DevModel hm;                 // host copy
   bool have_model = false, have_mocap = false;
-  int G = 16, block = 64, nv = 0;
+  int G = 16, block = 128, nv = 0;
   DevModel* d_model = nullptr;
   float* state_f = nullptr;
   int* state_i = nullptr;
@@ -283,7 +283,7 @@ extern "C" int drl_upload_model(DrlEnv* e, const DrlWalkerModel* m) {
   d.seed = c.seed; d.env_id_offset = c.env_id_offset;
   e->nv = m->nv;
   e->G = G;
-  e->block = 64;
+  e->block = 128;
   CUDA_TRY(cudaSetDevice(c.device));
   const size_t N = (size_t)c.num_envs;
   if (!e->d_model) {

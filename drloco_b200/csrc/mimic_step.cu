@@ -885,7 +885,8 @@ __global__ void __launch_bounds__(128, 4) mimic_step_kernel(const StepArgs A, co
   // a warp whose second environment is past the end recomputes the last valid one with all stores disabled
   const bool live = env_raw < A.num_envs;
   const int env = live ? env_raw : A.num_envs - 1;
-  if (blockIdx.x * epb + (threadIdx.x & ~31) / G >= A.num_envs) return;   // whole warp out of range
+  // (warps entirely past the end keep running on the clamped environment: the CTA-wide barriers in the substep loop
+  //  need every warp, and only the last CTA has such warps)
   EnvSmem<G>& E = envs[eib];
   LaneConst L;
   L.l = threadIdx.x % G;
@@ -983,6 +984,9 @@ __global__ void __launch_bounds__(128, 4) mimic_step_kernel(const StepArgs A, co
       float accq = 0.f, accv = 0.f;
 #pragma unroll 1
       for (int st = 0; st < 4; st++) {
+        // keep the warps of a CTA within one evaluation of each other: they then share instruction-cache lines
+        // (the dynamics evaluation is ~80 KB of straight-line code); measured +3 %
+        __syncthreads();
         forward_dynamics<NV, G, DBG>(M, E, L, q, v, tau, a, AS, cnt, dbgp);
         const float bw = (st == 0 || st == 3) ? (1.f / 6.f) : (1.f / 3.f);
         accq = fmaf(bw, v, accq);

@@ -986,6 +986,7 @@ __global__ void __launch_bounds__(128, 4) mimic_step_kernel(const StepArgs A, co
       for (int st = 0; st < 4; st++) {
         // keep the warps of a CTA within one evaluation of each other: they then share instruction-cache lines
         // (the dynamics evaluation is ~80 KB of straight-line code); measured +3 %
+        // (one barrier per substep instead of per stage loses the gain; a second barrier inside the evaluation adds none)
         __syncthreads();
         forward_dynamics<NV, G, DBG>(M, E, L, q, v, tau, a, AS, cnt, dbgp);
         const float bw = (st == 0 || st == 3) ? (1.f / 6.f) : (1.f / 3.f);

@@ -492,7 +492,7 @@ extern "C" int drl_debug_set(DrlEnv* e, int32_t frame_skip_override, int32_t blo
   if (!e) return fail(DRL_ERR_INVALID, "drl_debug_set: null env");
   e->frame_skip_override = frame_skip_override;
   if (block_threads > 0) {
-    if (block_threads % e->G != 0 || block_threads > 128) return fail(DRL_ERR_INVALID, "drl_debug_set: bad block size");
+    if (block_threads % 32 != 0 || block_threads > 128) return fail(DRL_ERR_INVALID, "drl_debug_set: block size must be 32, 64, 96 or 128");
     e->block = block_threads;
   }
   if (enable_dump && !e->debug) {

@@ -1215,14 +1215,18 @@ static cudaError_t launch_one(const StepArgs& a, int reset_only, int block, cuda
   const int epb = block / G;
   const size_t smem = step_smem_bytes(G, epb);
   auto kern = mimic_step_kernel<NV, G, RK4, DBG>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  // function attributes are per device: set them once for every device this process launches on
+  static unsigned long long attr_done = 0ull;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (!((attr_done >> (dev & 63)) & 1ull)) {
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return e;
     // all of the unified L1/shared array as shared memory: residency is bounded by the per-env scratch, not by L1 hits
     e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return e;
-    attr_done = true;
+    attr_done |= 1ull << (dev & 63);
   }
   const int grid = (a.num_envs + epb - 1) / epb;
   kern<<<grid, block, smem, st>>>(a, reset_only);

@@ -176,7 +176,8 @@ class PPO:
 
 
 @torch.no_grad()
-def evaluate_walking(policy: ActorCritic, train_env, n_episodes: int = 20, min_stable_distance: float = 15.0):
+def evaluate_walking(policy: ActorCritic, train_env, n_episodes: int = 20, min_stable_distance: float = 15.0,
+                     steady_state_counters: bool = False):
     """Deterministic evaluation in the spirit of reference ``TrainingMonitor.eval_walking`` (callback.py:272-390):
     ``n_episodes`` episodes from the deterministic initial states (step i of the mocap at 75 % of the step,
     straight_walk_trajecs.py:237-265), deterministic actions, frozen normalisation statistics; reports walked distance,
@@ -193,6 +194,15 @@ def evaluate_walking(policy: ActorCritic, train_env, n_episodes: int = 20, min_s
     istep = (np.arange(n_episodes) % t.n_steps).astype(np.int32)
     pos = ((3 * t.step_len[istep]) // 4).astype(np.int32)
     obs = vn.reset_tensor(inject=(istep, pos)).clone()
+    if steady_state_counters:
+        # count_steps_same_vel is never reset in the reference (Q3): after ~30 mocap steps of an env's lifetime the
+        # desired-velocity observation is stuck at step_vel[0], which is what the policy saw for nearly all of its
+        # training.  A freshly built evaluation env starts the counter at 1 and feeds step_vel[i_step] instead; this
+        # switch reproduces the training-time (steady-state) counter in the evaluation env.
+        q, v, cur = env.get_state()
+        cur[:, 2] = 10 ** 6
+        env.set_state(None, None, cur)
+        obs = vn.reset_tensor(inject=(istep, pos)).clone()
     n = n_episodes
     alive = torch.ones(n, dtype=torch.bool, device=venv.device)
     ep_len = torch.zeros(n, device=venv.device)

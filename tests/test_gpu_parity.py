@@ -428,3 +428,19 @@ def test_w165_config4_invariants():
     st = env.stats()
     assert st["env_steps"] == n * steps and st["episodes"] == done_total
     env.close()
+
+
+def test_ppo_consumer_runs_on_device_rollouts():
+    """next-tier smoke: the PPO loop (drloco_b200/ppo.py) consumes the tensor API end to end and produces finite updates."""
+    from drloco_b200.ppo import PPO, PPOConfig, evaluate_walking
+    from drloco_b200.vec_env import vec_env
+    env = vec_env(W3D, num_envs=256, seed=1)
+    cfg = PPOConfig(batch_size=256 * 16, minibatch_size=1024, total_steps=256 * 16 * 3)
+    agent = PPO(env, cfg, seed=0).learn(log_every=1)
+    assert agent.num_timesteps == 256 * 16 * 3 and len(agent.log) == 3
+    for row in agent.log:
+        assert all(np.isfinite(v) for v in row.values())
+        assert 0.0 < row["mean_step_reward"] <= 1.2
+    ev = evaluate_walking(agent.policy, env, n_episodes=4)
+    assert ev["n_episodes"] == 4 and ev["min_episode_duration"] >= 1 and np.isfinite(ev["mean_walked_distance"])
+    env.close()

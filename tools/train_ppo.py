@@ -42,10 +42,12 @@ def main():
     torch.cuda.synchronize()
     ev = evaluate_walking(agent.policy, env)
     print("evaluation (deterministic policy, 20 deterministic inits):", json.dumps(ev), flush=True)
+    ev2 = evaluate_walking(agent.policy, env, steady_state_counters=True)
+    print("evaluation with the training-time desired-velocity counter (Q3):", json.dumps(ev2), flush=True)
     os.makedirs(os.path.dirname(args.out) or ".", exist_ok=True)
     with open(args.out, "w") as f:
         json.dump({"envs": args.envs, "total_steps": agent.num_timesteps, "wall_s": time.time() - t0,
-                   "config": {k: v for k, v in vars(cfg).items()}, "curve": agent.log, "evaluation": ev}, f, indent=1)
+                   "config": {k: v for k, v in vars(cfg).items()}, "curve": agent.log, "evaluation": ev, "evaluation_steady_state_counters": ev2}, f, indent=1)
     print("done: %.1f s, %.2e env-steps/s incl. learning" % (time.time() - t0, agent.num_timesteps / (time.time() - t0)))
 
 

@@ -113,6 +113,7 @@ extern "C" int drl_upload_model(DrlEnv* e, const DrlWalkerModel* m) {
   if (m->nu <= 0 || m->nu > kMaxAct || m->nu != c.act_dim) return fail(DRL_ERR_INVALID, "model: nu != act_dim");
   if (m->nv != 14 && m->nv != 19)
     return fail(DRL_ERR_UNSUPPORTED, "model: kernels are instantiated for nv = 14 and nv = 19 (got %d)", m->nv);
+  if (e->have_model) return fail(DRL_ERR_STATE, "drl_upload_model: a model is already attached to this env");
   DevModel& d = e->hm;
   memset(&d, 0, sizeof d);
   d.nv = m->nv; d.nb = m->nb; d.nu = m->nu; d.nsite = m->n_site;

@@ -336,6 +336,29 @@ def test_vecnormalize_matches_sb3_semantics():
     env.close()
 
 
+def test_vec_env_factory_save_load(tmp_path):
+    """drop-in for drloco.common.utils.vec_env / save_model / load_env (utils.py:97-134,175-192,234-240)."""
+    from drloco_b200.vec_env import vec_env
+    env = vec_env(W3D, num_envs=32, seed=3, norm_rew=True)
+    env.reset()
+    rng = np.random.default_rng(0)
+    for _ in range(5):
+        env.step(rng.uniform(-1, 1, (32, 8)).astype(np.float32))
+    path = str(tmp_path / "env_ckpt")
+    env.save(path)
+    env2 = vec_env(W3D, num_envs=1, seed=3, norm_rew=True, load_path=path)      # the callback's 1-env eval env
+    np.testing.assert_array_equal(env2.obs_rms.mean, env.obs_rms.mean)
+    np.testing.assert_array_equal(env2.obs_rms.var, env.obs_rms.var)
+    assert env2.ret_rms.var == env.ret_rms.var and env2.num_envs == 1
+    env2.training = False
+    env2.env_method("activate_evaluation")
+    o = env2.reset()
+    assert o.shape == (1, 29) and np.isfinite(o).all() and np.abs(o).max() <= 10.0
+    assert env.get_attr("ep_len_smoothed") == env.venv.get_attr("ep_len_smoothed")
+    env.close()
+    env2.close()
+
+
 # --------------------------------------------------------------------------------------------------------------------
 # full-size properties (BASELINE.json configs[1]: 4096 envs) — size-independent invariants
 # --------------------------------------------------------------------------------------------------------------------

@@ -51,7 +51,8 @@ struct DrlEnv {
   double* state_d = nullptr;
   float* extras_last = nullptr;
   double* stats = nullptr;
-  float *ref = nullptr, *step_vel = nullptr, *step_last_comx = nullptr, *des_vel_prefix = nullptr;
+  float *ref = nullptr, *step_vel = nullptr, *step_last_comx = nullptr;
+  double* des_vel_prefix = nullptr;   // float64: differences of long prefix sums lose ~1e-5 in float32
   int *step_off = nullptr, *step_len = nullptr;
   unsigned char* left_step = nullptr;
   int* ring_len = nullptr;

@@ -90,7 +90,7 @@ struct StepArgs {
   const unsigned char* left_step;
   const float* step_vel;
   const float* step_last_comx;
-  const float* des_vel_prefix;       // [n_samples+1][2] or null
+  const double* des_vel_prefix;      // [n_samples+1][2] or null (float64 prefix sums)
   // io
   const float* actions;              // [N][act_dim]
   float* obs;                        // [N][obs_dim]

@@ -766,8 +766,8 @@ __device__ __forceinline__ void desired_velocity(const DevModel& M, const StepAr
     if (n <= 0) {
       d0 = d1 = nanf("");   // mean of an empty slice (Q23)
     } else {
-      d0 = (A.des_vel_prefix[2 * end] - A.des_vel_prefix[2 * c.pos]) / (float)n;
-      d1 = (A.des_vel_prefix[2 * end + 1] - A.des_vel_prefix[2 * c.pos + 1]) / (float)n;
+      d0 = (float)((A.des_vel_prefix[2 * end] - A.des_vel_prefix[2 * c.pos]) / (double)n);
+      d1 = (float)((A.des_vel_prefix[2 * end + 1] - A.des_vel_prefix[2 * c.pos + 1]) / (double)n);
     }
   }
 }

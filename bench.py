@@ -334,7 +334,8 @@ def main():
                      "algo_flop_per_env_step": algo_flop},
             "episode_stats": {"episodes": stats["episodes"], "mean_ep_len": stats["ep_len_sum"] / max(1.0, stats["episodes"]),
                               "reset_rate_per_env_step": stats["episodes"] / max(1.0, stats["env_steps"]),
-                              "solver_iters_per_eval": stats["solver_iters"] / max(1.0, stats["dyn_evals"])},
+                              "solver_iters_per_eval": stats["solver_iters"] / max(1.0, stats["dyn_evals"]),
+                              "solver_capped_frac": stats["solver_capped"] / max(1.0, stats["dyn_evals"])},
         }
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_single()

@@ -20,8 +20,8 @@ EXTRA_NAMES = ("pos_rew", "vel_rew", "com_rew", "walked_distance", "mean_abs_tor
 EXTRA_COUNT = 16
 STAT_NAMES = ("episodes", "ep_len_sum", "ep_ret_sum", "ep_mean_rew_sum", "pos_rew_sum", "vel_rew_sum", "com_rew_sum",
               "rew_steps", "moved_distance_sum", "abs_torque_sum", "env_steps", "blowups", "falls", "timeouts",
-              "solver_iters", "dyn_evals")
-STATS_COUNT = 16
+              "solver_iters", "dyn_evals", "solver_capped")
+STATS_COUNT = 17
 
 d, i32 = C.c_double, C.c_int32
 

@@ -142,7 +142,7 @@ struct LaneConst {
 };
 
 struct Counters {
-  int evals, iters;
+  int evals, iters, capped;
 };
 
 // active set carried from one dynamics evaluation to the next (lane <-> contact candidate is a fixed mapping)
@@ -672,6 +672,7 @@ __device__ __forceinline__ void forward_dynamics(const DevModel& M, EnvSmem<G>& 
       AS.lbit = nl;
     }
     if (!__any_sync(kFull, changed)) break;
+    if (it == kMaxSolverIter - 1 && env_any(changed, L.emask)) cnt.capped++;
   }
   AS.prev_act = (cact[0] ? 1u : 0u) | (cact[1] ? 2u : 0u);
   AS.prev_lim = lsg != 0.f;
@@ -907,7 +908,7 @@ __global__ void __launch_bounds__(128, 4) mimic_step_kernel(const StepArgs A, co
   c.i_step = si[kCurIstep]; c.pos = si[kCurPos]; c.count = si[kCurCount]; c.ep_dur = si[kCurEpDur];
   c.rsi_step = si[kCurRsiStep]; c.n_det = si[kCurNDet]; c.resets = si[kCurResets]; c.flags = si[kCurFlags];
   float dist = sf[3 * G + kMiscDist], zoff = sf[3 * G + kMiscZoff];
-  Counters cnt = {0, 0};
+  Counters cnt = {0, 0, 0};
   // active set of the last evaluation of the previous step (bits 0-3 / 4-7: pyramid rows of the two candidates,
   // 8-9: candidates in contact, 10: limit row active, 11: limit violated)
   int* sa = A.state_as + (size_t)env * G;
@@ -1092,6 +1093,7 @@ __global__ void __launch_bounds__(128, 4) mimic_step_kernel(const StepArgs A, co
     atomicAdd(&A.stats[DRL_STAT_ABS_TORQUE_SUM], (double)mean_abs_torque);
     atomicAdd(&A.stats[DRL_STAT_SOLVER_ITERS], (double)cnt.iters);
     atomicAdd(&A.stats[DRL_STAT_DYN_EVALS], (double)cnt.evals);
+    if (cnt.capped) atomicAdd(&A.stats[DRL_STAT_SOLVER_CAPPED], (double)cnt.capped);
     if (A.extras) {
       float* ex = A.extras + (size_t)env * 16;
       ex[0] = pos_rew; ex[1] = vel_rew; ex[2] = com_rew; ex[3] = walked; ex[4] = mean_abs_torque;

@@ -181,7 +181,8 @@ typedef enum {
   DRL_STAT_MOVED_DISTANCE_SUM = 8, DRL_STAT_ABS_TORQUE_SUM = 9,
   DRL_STAT_ENV_STEPS = 10, DRL_STAT_BLOWUPS = 11, DRL_STAT_FALLS = 12, DRL_STAT_TIMEOUTS = 13,
   DRL_STAT_SOLVER_ITERS = 14, DRL_STAT_DYN_EVALS = 15,
-  DRL_STATS_COUNT = 16
+  DRL_STAT_SOLVER_CAPPED = 16,   /* evaluations whose active-set iteration stopped at the cap instead of converging */
+  DRL_STATS_COUNT = 17
 } DrlStat;
 int drl_get_stats(DrlEnv* env, double* stats, void* stream);
 int drl_reset_stats(DrlEnv* env, void* stream);

@@ -126,6 +126,7 @@ extern "C" int drl_upload_model(DrlEnv* e, const DrlWalkerModel* m) {
   d.Bc = (float)(2.0 / (dmax * tc));
   d.imp_d0 = (float)d0; d.imp_dmax = (float)dmax; d.imp_width = (float)fmax(1e-15, m->solimp[2]);
   d.imp_mid = (float)fmin(0.9999, fmax(0.0001, m->solimp[3])); d.imp_power = (float)fmax(1.0, m->solimp[4]);
+  d.imp_inv_width = 1.f / d.imp_width; d.imp_inv_mid = 1.f / d.imp_mid; d.imp_inv_1mmid = 1.f / (1.f - d.imp_mid);
   if (m->body_parent[0] != -1) return fail(DRL_ERR_INVALID, "model: body 0 must be the root");
   d.root_z0 = (float)m->body_pos[0][2];
   int depth[kMaxBody];

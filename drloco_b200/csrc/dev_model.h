@@ -15,12 +15,14 @@ constexpr int kMaxSite = 16;
 constexpr int kMaxLevel = 6;
 constexpr int kMaxObs = 64;
 
-struct DevModel {
+// alignas(16): the step kernel stages this struct into shared memory in 16-byte chunks (sizeof must be a multiple of 16)
+struct alignas(16) DevModel {
   // sizes
   int nv, nb, nu, ncand, nbox_cand, nsite, nlevel, nslide;
   float timestep, gravity_z;
   float Kc, Bc;                      // 1/(dmax^2 tc^2 dr^2), 2/(dmax tc)  (solref)
   float imp_d0, imp_dmax, imp_width, imp_mid, imp_power;
+  float imp_inv_width, imp_inv_mid, imp_inv_1mmid;   // reciprocals used by the power-2 impedance curve
   float root_z0;                     // body_pos[root].z
   // bodies
   int body_parent[kMaxBody];
@@ -64,6 +66,8 @@ struct DevModel {
   unsigned long long seed;
   long long env_id_offset;
 };
+
+static_assert(sizeof(DevModel) % 16 == 0, "DevModel is copied in int4 chunks");
 
 // per-env persistent state rows (see DESIGN.md "data layout in HBM")
 constexpr int kMiscDist = 0, kMiscZoff = 1, kMiscWalked = 2, kMiscEpRet = 3, kMiscEpTor = 4, kMiscPrevPos = 5,

@@ -110,6 +110,13 @@ __device__ __forceinline__ Vec6 inertia_mul(const float* I, const Vec6& t) {
   return r;
 }
 
+// reciprocal: hardware approximation + one Newton step (relative error ~1e-7, no IEEE-division slow path)
+__device__ __forceinline__ float fast_rcp(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return fmaf(r, fmaf(-x, r, 1.f), r);
+}
+
 // general solimp power (MuJoCo default is 2, handled inline by impedance())
 __device__ __noinline__ float impedance_pow(float x, float mid, float power) {
   return (x <= mid) ? powf(x, power) / powf(mid, power - 1.f)
@@ -117,12 +124,12 @@ __device__ __noinline__ float impedance_pow(float x, float mid, float power) {
 }
 
 __device__ __forceinline__ float impedance(const DevModel& M, float dist) {
-  float x = fabsf(dist) / M.imp_width;
+  float x = fabsf(dist) * M.imp_inv_width;
   if (x >= 1.f) return M.imp_dmax;
   if (x <= 0.f) return M.imp_d0;
   float y;
   if (M.imp_power == 2.f) {
-    y = (x <= M.imp_mid) ? x * x / M.imp_mid : 1.f - (1.f - x) * (1.f - x) / (1.f - M.imp_mid);
+    y = (x <= M.imp_mid) ? x * x * M.imp_inv_mid : 1.f - (1.f - x) * (1.f - x) * M.imp_inv_1mmid;
   } else if (M.imp_power == 1.f) {
     y = x;
   } else {
@@ -155,13 +162,6 @@ struct ActiveSet {
 // symmetric 6x6 index into 21 packed entries (i <= j)
 __device__ __forceinline__ constexpr int sym6(int i, int j) {
   return (i <= j) ? (i * 6 - (i * (i - 1)) / 2 + (j - i)) : (j * 6 - (j * (j - 1)) / 2 + (i - j));
-}
-
-// reciprocal: hardware approximation + one Newton step (relative error ~1e-7, no IEEE-division slow path)
-__device__ __forceinline__ float fast_rcp(float x) {
-  float r;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-  return fmaf(r, fmaf(-x, r, 1.f), r);
 }
 
 // pop the two lowest set bits of a mask (i1 = i0 and second = false when only one is left): the chain loops below
@@ -350,14 +350,16 @@ __device__ __forceinline__ void forward_dynamics(const DevModel& M, EnvSmem<G>& 
   if (L.isbody) {
     float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
     float2 a2 = make_float2(0.f, 0.f);
-    for (unsigned mk = M.body_sub[l]; mk; mk &= mk - 1) {
-      const int b = __ffs(mk) - 1;
-      const float4 x0 = *reinterpret_cast<const float4*>(E.Ib[b]);
-      const float4 x1 = *reinterpret_cast<const float4*>(E.Ib[b] + 4);
-      const float2 x2 = *reinterpret_cast<const float2*>(E.Ib[b] + 8);
-      a0.x += x0.x; a0.y += x0.y; a0.z += x0.z; a0.w += x0.w;
-      a1.x += x1.x; a1.y += x1.y; a1.z += x1.z; a1.w += x1.w;
-      a2.x += x2.x; a2.y += x2.y;
+    for (unsigned mk = M.body_sub[l]; mk;) {
+      int b0, b1; bool two;
+      pop2(mk, b0, b1, two);
+      const float w = two ? 1.f : 0.f;
+      const float4 x0 = *reinterpret_cast<const float4*>(E.Ib[b0]), y0 = *reinterpret_cast<const float4*>(E.Ib[b1]);
+      const float4 x1 = *reinterpret_cast<const float4*>(E.Ib[b0] + 4), y1 = *reinterpret_cast<const float4*>(E.Ib[b1] + 4);
+      const float2 x2 = *reinterpret_cast<const float2*>(E.Ib[b0] + 8), y2 = *reinterpret_cast<const float2*>(E.Ib[b1] + 8);
+      a0.x += x0.x + w * y0.x; a0.y += x0.y + w * y0.y; a0.z += x0.z + w * y0.z; a0.w += x0.w + w * y0.w;
+      a1.x += x1.x + w * y1.x; a1.y += x1.y + w * y1.y; a1.z += x1.z + w * y1.z; a1.w += x1.w + w * y1.w;
+      a2.x += x2.x + w * y2.x; a2.y += x2.y + w * y2.y;
     }
     *reinterpret_cast<float4*>(E.Ic[l]) = a0;
     *reinterpret_cast<float4*>(E.Ic[l] + 4) = a1;
@@ -436,8 +438,9 @@ __device__ __forceinline__ void forward_dynamics(const DevModel& M, EnvSmem<G>& 
     if (act) {
       const float mu = M.cand_mu[s];
       const float imp = impedance(M, dist);
-      const float Rn = fmaxf(kMinVal, (1.f - imp) / imp * M.body_invw_tran[b] * (1.f + mu * mu));
-      cD[ps] = 1.f / (2.f * mu * mu * Rn);
+      // D = 1 / (2 mu^2 R_n),  R_n = (1-imp)/imp * invweight * (1 + mu^2)
+      const float Rn = fmaxf(kMinVal, (1.f - imp) * M.body_invw_tran[b] * (1.f + mu * mu));
+      cD[ps] = imp * fast_rcp(2.f * mu * mu * Rn);
       cmu[ps] = mu;
       conmask |= 1u << b;
       // reference acceleration of the four pyramid rows: aref = -B (J v) - K imp dist   (E.V is complete since step 4)
@@ -488,7 +491,7 @@ __device__ __forceinline__ void forward_dynamics(const DevModel& M, EnvSmem<G>& 
     else if (q > L.hi) { lsg = -1.f; dist = L.hi - q; }
     if (lsg != 0.f) {
       const float imp = impedance(M, dist);
-      lD = 1.f / fmaxf(kMinVal, (1.f - imp) / imp * L.invw);
+      lD = imp * fast_rcp(fmaxf(kMinVal, (1.f - imp) * L.invw));
       laref = -M.Bc * lsg * v - M.Kc * imp * dist;
     }
   }

@@ -61,6 +61,7 @@ struct EnvSmem {
     float Mt[kMaxBody * 56];
   };
   float obsbuf[kMaxObs];
+  float Mc[(G == 16 ? 14 : 19) * G];   // mass-matrix column of each lane: Mc[r * G + l] (kept out of registers)
 };
 
 __device__ __forceinline__ void cross3(float& rx, float& ry, float& rz, float ax, float ay, float az, float bx,
@@ -247,7 +248,8 @@ __device__ __forceinline__ void tree_kinematics(const DevModel& M, EnvSmem<G>& E
 // the transposed entries through shared memory (odd row stride: the row-wise store and the column-wise load are both
 // conflict-free).  E.Mt aliases V/A/T/W/U: callers guarantee those are dead; ends with a barrier.
 template <int NV, int G>
-__device__ __forceinline__ void mass_column(EnvSmem<G>& E, const LaneConst& L, const Vec6& S, float (&Mcol)[NV]) {
+__device__ __forceinline__ void mass_column(EnvSmem<G>& E, const LaneConst& L, const Vec6& S) {
+  float Mcol[NV];
   constexpr int kMs = (NV % 2 == 0) ? NV + 1 : NV + 2;
   static_assert(NV * kMs <= (int)(sizeof(E.Mt) / sizeof(float)), "Mt too small");
   const int l = L.l;
@@ -263,6 +265,7 @@ __device__ __forceinline__ void mass_column(EnvSmem<G>& E, const LaneConst& L, c
   for (int r = 0; r < NV; r++) {
     if (L.isdof && r < l) Mcol[r] = E.Mt[l * kMs + r];
     if (r == l) Mcol[r] += L.armature;
+    E.Mc[r * G + l] = Mcol[r];
   }
   __syncwarp();
 }
@@ -477,11 +480,10 @@ __device__ __forceinline__ void forward_dynamics(const DevModel& M, EnvSmem<G>& 
   }
   __syncwarp();
   // ---- 7. mass-matrix column ---------------------------------------------------------------------------------
-  float Mcol[NV];
-  mass_column<NV, G>(E, L, S, Mcol);
+  mass_column<NV, G>(E, L, S);
   if (DBG) {
 #pragma unroll
-    for (int r = 0; r < NV; r++) dbg[(2 + r) * 32 + l] = Mcol[r];
+    for (int r = 0; r < NV; r++) dbg[(2 + r) * 32 + l] = E.Mc[r * G + l];
   }
   // ---- joint limits ---------------------------------------------------------------------------------------------
   float lsg = 0.f, lD = 0.f, laref = 0.f;
@@ -598,7 +600,7 @@ __device__ __forceinline__ void forward_dynamics(const DevModel& M, EnvSmem<G>& 
     }
     // Hessian column
 #pragma unroll
-    for (int r = 0; r < NV; r++) H[r] = Mcol[r];
+    for (int r = 0; r < NV; r++) H[r] = E.Mc[r * G + l];
     H[NV] = rhs0;
     if (constrained && L.isdof) {
       for (unsigned mk = conmask; mk; mk &= mk - 1) {
@@ -1013,13 +1015,12 @@ __global__ void __launch_bounds__(128, 4) mimic_step_kernel(const StepArgs A, co
       float Hc[NV + 1];
       float Ma = 0.f;
       {
-        float Mc[NV];
-        const Vec6 S = L.isdof ? ld6(E.S[l]) : Vec6{0, 0, 0, 0, 0, 0};
-        mass_column<NV, G>(E, L, S, Mc);
+        // E.Mc still holds this lane's column from the evaluation above
 #pragma unroll
         for (int r = 0; r < NV; r++) {
-          Ma = fmaf(Mc[r], E.acc[r], Ma);
-          Hc[r] = Mc[r] + (r == l ? h * L.damping : 0.f);
+          const float m = E.Mc[r * G + l];
+          Ma = fmaf(m, E.acc[r], Ma);
+          Hc[r] = m + (r == l ? h * L.damping : 0.f);
         }
       }
       Hc[NV] = Ma;

@@ -60,6 +60,9 @@ struct DrlEnv {
   unsigned long long* ring_head = nullptr;
   int ring_cap = 1 << 16;
   int eval_mode = 0;
+  float* speed_profile = nullptr;
+  int speed_profile_len = 0;
+  int playback = 0;
   int frame_skip_override = -1;
   float* debug = nullptr;
 };
@@ -90,7 +93,7 @@ extern "C" int drl_destroy(DrlEnv* e) {
   cudaSetDevice(e->cfg.device);
   void* ptrs[] = {e->d_model, e->state_f, e->state_i, e->state_as, e->state_d, e->extras_last, e->stats, e->ref, e->step_vel,
                   e->step_last_comx, e->des_vel_prefix, e->step_off, e->step_len, e->left_step, e->ring_len,
-                  e->ring_ret, e->ring_head, e->debug};
+                  e->ring_ret, e->ring_head, e->debug, e->speed_profile};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   delete e;
@@ -387,6 +390,10 @@ static StepArgs make_args(DrlEnv* e) {
   a.extras = e->extras_last; a.stats = e->stats;
   a.ring_len = e->ring_len; a.ring_ret = e->ring_ret; a.ring_head = e->ring_head; a.ring_cap = e->ring_cap;
   a.eval_mode = e->eval_mode;
+  a.speed_profile = e->speed_profile_len > 0 ? e->speed_profile : nullptr;
+  a.speed_profile_len = e->speed_profile_len;
+  a.playback = e->playback;
+  if (e->playback) a.frame_skip = 0;
   a.debug = e->debug;
   return a;
 }
@@ -476,6 +483,29 @@ extern "C" int drl_get_episode_ring(DrlEnv* e, int32_t* ep_len, float* ep_ret, i
 extern "C" int drl_set_eval_mode(DrlEnv* e, int32_t on) {
   if (!e) return fail(DRL_ERR_INVALID, "drl_set_eval_mode: null env");
   e->eval_mode = on ? 1 : 0;
+  return DRL_OK;
+}
+
+extern "C" int drl_set_playback(DrlEnv* e, int32_t on) {
+  if (!e) return fail(DRL_ERR_INVALID, "drl_set_playback: null env");
+  e->playback = on ? 1 : 0;
+  return DRL_OK;
+}
+
+extern "C" int drl_set_speed_profile(DrlEnv* e, const float* speeds, int32_t n) {
+  if (!e) return fail(DRL_ERR_INVALID, "drl_set_speed_profile: null env");
+  if (n < 0 || (n > 0 && !speeds)) return fail(DRL_ERR_INVALID, "drl_set_speed_profile: n=%d with %s table", n,
+                                               speeds ? "a" : "a null");
+  CUDA_TRY(cudaSetDevice(e->cfg.device));
+  CUDA_TRY(cudaDeviceSynchronize());   // the previous table may still be read by enqueued steps
+  if (e->speed_profile) CUDA_TRY(cudaFree(e->speed_profile));
+  e->speed_profile = nullptr;
+  e->speed_profile_len = 0;
+  if (n > 0) {
+    CUDA_TRY(cudaMalloc(&e->speed_profile, (size_t)n * sizeof(float)));
+    CUDA_TRY(cudaMemcpy(e->speed_profile, speeds, (size_t)n * sizeof(float), cudaMemcpyHostToDevice));
+    e->speed_profile_len = n;
+  }
   return DRL_OK;
 }
 

@@ -111,6 +111,9 @@ struct StepArgs {
   unsigned long long* ring_head;
   int ring_cap;
   int eval_mode;
+  const float* speed_profile;        // desired speed per control step (activate_speed_control), null when off
+  int speed_profile_len;
+  int playback;                      // kinematic playback: the state is set from the mocap instead of simulated
   float* debug;                      // nullable: per-env dump of one forward evaluation (tests)
 };
 

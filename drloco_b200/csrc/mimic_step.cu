@@ -761,7 +761,9 @@ __device__ __forceinline__ float group_min(float x) {
 __device__ __forceinline__ void desired_velocity(const DevModel& M, const StepArgs& A, const Cursor& c, float& d0,
                                                  float& d1) {
   d1 = 0.f;
-  if (M.cursor_mode == DRL_CURSOR_STEPWISE) {
+  if (A.speed_profile != nullptr) {            // mimic_env.py:406-408 (scalar profile; second component stays 0)
+    d0 = A.speed_profile[c.ep_dur % A.speed_profile_len];
+  } else if (M.cursor_mode == DRL_CURSOR_STEPWISE) {
     int idx = c.i_step - c.count + 1;
     d0 = A.step_vel[idx < 0 ? 0 : idx];
   } else {
@@ -826,7 +828,7 @@ __device__ __noinline__ void reset_env(const DevModel& M, const StepArgs& A, Env
                                        int env, Cursor& c, float& q, float& v, float& dist, float& zoff) {
   const int l = L.l;
   c.ep_dur = 0;
-  if (A.eval_mode) {                           // straight:237-265 / base:69-77
+  if (A.eval_mode || A.speed_profile != nullptr) {   // mimic_env.py:536-537; straight:237-265 / base:69-77
     if (M.cursor_mode == DRL_CURSOR_STEPWISE) {
       c.i_step = c.n_det;
       c.pos = (3 * A.step_len[c.i_step]) / 4;
@@ -1044,6 +1046,11 @@ __global__ void __launch_bounds__(128, 4) mimic_step_kernel(const StepArgs A, co
   bool done;
   const int ep_dur_before = c.ep_dur;
   cursor_next(M, A, c, dist);                                   // mimic_env.py:96
+  if (A.playback) {                                             // set_joint_kinematics_in_sim (mimic_env.py:273-293)
+    float rq, rv;
+    ref_lookup(M, A, c, dist, zoff, l, G, L.isdof, rq, rv);
+    if (L.isdof) { q = rq; v = rv; }
+  }
   build_obs<G>(M, A, E, L, c, q, v, phase0, des0);               // mimic_env.py:99
   c.ep_dur += 1;                                                // mimic_env.py:106
   {                                                             // mimic_env.py:131-139

@@ -83,6 +83,16 @@ class WalkerSpec:
         return oi, osn, ai, asn
 
 
+def speed_profile(speeds, speed_profile_duration, control_freq) -> np.ndarray:
+    """Desired walking speed per control step, as MimicEnv.activate_speed_control builds it (mimic_env.py:313-322):
+    the profile is split into len(speeds)-1 regions of equal length, each a linspace between neighbouring speeds."""
+    speeds = list(speeds)
+    n_sections = len(speeds) - 1
+    assert n_sections >= 1, "a speed profile needs at least two speeds"
+    region = int(speed_profile_duration * control_freq / n_sections)
+    return np.concatenate([np.linspace(speeds[i], speeds[i + 1], region) for i in range(n_sections)])
+
+
 def make_spec(cfg: Optional[cfgm.EnvConfig] = None, mocap_path: Optional[str] = None) -> WalkerSpec:
     """env id -> everything the device needs (reference drloco/mujoco/config.py:9-10 ``env_map``)."""
     cfg = cfg or cfgm.EnvConfig()

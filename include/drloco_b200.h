@@ -195,6 +195,18 @@ int drl_get_episode_ring(DrlEnv* env, int32_t* ep_len, float* ep_ret, int32_t ca
 /* MimicEnv.activate_evaluation (mimic_env.py:245): deterministic init states (straight_walk_trajecs.py:237-265) */
 int drl_set_eval_mode(DrlEnv* env, int32_t on);
 
+/* MimicEnv.activate_speed_control (mimic_env.py:298-327): from now on the desired-velocity observation of every env is
+ * speeds[ep_dur % n] (mimic_env.py:406-408) and resets use the deterministic init state (mimic_env.py:536-537).
+ * `speeds` is a HOST array with one desired speed per control step (the host builds it with the reference's
+ * linspace regions); n = 0 switches speed control off.  Synchronises the device (not for the stepping loop). */
+int drl_set_speed_profile(DrlEnv* env, const float* speeds, int32_t n);
+
+/* MimicEnv.playback_ref_trajectories (mimic_env.py:265-282): while on, drl_step skips the physics and, after
+ * refs.next(), sets qpos / qvel from the mocap (set_joint_kinematics_in_sim, mimic_env.py:284-293) before the
+ * observation, reward and termination logic run.  A kinematic check of tables, cursor and ground shift: the imitation
+ * reward of every such step is its maximum.  Rendering is not part of this library. */
+int drl_set_playback(DrlEnv* env, int32_t on);
+
 /* test / tuning hooks: frame_skip_override >= 0 replaces cfg.frame_skip (0 = environment logic only, used to test the
  * reward / cursor / reset path on injected states); block_threads > 0 sets the CTA size; enable_dump keeps, per env, the
  * intermediate results of the last dynamics evaluation (mass matrix, bias force, qacc) for drl_debug_read (host buffer). */

@@ -151,6 +151,9 @@ class OracleMimicEnv:
         self.ep_dur = 0
         self.walked_distance = 0.0
         self._EVAL_MODEL = False
+        self._FOLLOW_DESIRED_SPEED_PROFILE = False           # mimic_env.py:33
+        self.desired_walking_speed_trajectory = None
+        self._PLAYBACK_REF_TRAJECS = False                   # mimic_env.py:266
         self.mirr_obs_idx, self.mirr_obs_sign, self.mirr_act_idx, self.mirr_act_sign = spec.mirror_tables()
         self.last_ctrl = np.zeros(m.nu)
 
@@ -201,8 +204,22 @@ class OracleMimicEnv:
             out += [math.atan2(vel, -pos) / math.pi, math.sqrt(pos * pos + vel * vel) / 5]
         return out
 
+    def activate_speed_control(self, speeds=(1.0, 1.0), speed_profile_duration=10):   # mimic_env.py:298-322
+        self._FOLLOW_DESIRED_SPEED_PROFILE = True
+        n_sections = len(speeds) - 1
+        region = int(speed_profile_duration * self.cfg.ctrl_freq / n_sections)
+        self.desired_walking_speed_trajectory = np.concatenate(
+            [np.linspace(speeds[i], speeds[i + 1], region) for i in range(n_sections)])
+
     def _get_obs(self):                                      # mimic_env.py:403-437
-        des = self.refs.get_desired_walking_velocity_vector()
+        if self._FOLLOW_DESIRED_SPEED_PROFILE:               # mimic_env.py:406-408
+            # the reference then does `*self.desired_walking_speed` on this scalar and raises TypeError (Q26); the
+            # restatement follows the intent: the scalar fills the first desired-velocity slot, the others stay 0
+            prof = self.desired_walking_speed_trajectory
+            n_des = len(self.refs.get_desired_walking_velocity_vector())
+            des = [prof[self.ep_dur % len(prof)]] + [0.0] * (n_des - 1)
+        else:
+            des = self.refs.get_desired_walking_velocity_vector()
         phases = [self.refs.get_phase_variable()] if self.spec.phase_from_cursor else self.estimate_phase_vars()
         obs = np.array([*phases, *des, *self.qpos[1:], *self.qvel])
         if self.spec.mirror and self.refs.is_step_left():
@@ -218,10 +235,12 @@ class OracleMimicEnv:
         m = self.spec.model
         self.act_force = np.clip(np.clip(ctrl, m.act_ctrlrange[:, 0], m.act_ctrlrange[:, 1]) * m.act_gear,
                                  m.act_forcerange[:, 0], m.act_forcerange[:, 1])
-        if self.phys.step(self.qpos, self.qvel, ctrl, self.spec.frame_skip):
+        if not self._PLAYBACK_REF_TRAJECS and self.phys.step(self.qpos, self.qvel, ctrl, self.spec.frame_skip):
             obs = self.reset()                               # MujocoException path, mimic_env.py:86-91
             return obs, 0, True, {"blowup": True}
         self.refs.next()
+        if self._PLAYBACK_REF_TRAJECS:                       # body of the playback loop, mimic_env.py:273-275,284-293
+            self.qpos[:], self.qvel[:] = self.refs.get_qpos(), self.refs.get_qvel()
         obs = self._get_obs()
         self.ep_dur += 1
         vel_vec = np.clip(self.qvel[:2], -5.5, 5.5)          # mimic_env.py:131-139
@@ -234,7 +253,7 @@ class OracleMimicEnv:
     def reset(self, i_step=None, pos=None):                  # MujocoEnv.reset + mimic_env.py:526-572
         self.ep_dur = 0
         self.walked_distance = 0
-        if self._EVAL_MODEL:
+        if self._EVAL_MODEL or self._FOLLOW_DESIRED_SPEED_PROFILE:   # mimic_env.py:536-537
             self.refs.init_deterministic(self.cfg.eval_n_times)
         else:
             self.refs.init_random(i_step, pos)

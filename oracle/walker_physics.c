@@ -424,7 +424,7 @@ int orc_forward(const DrlWalkerModel* m, const double* q, const double* v, const
         nact[i] = s < 0;
         if (nact[i] != act[i]) same = 0;
       }
-      memcpy(act, nact, nrow);
+      if (nrow > 0) memcpy(act, nact, (size_t)nrow);
       if (same) { conv = 1; iters++; break; }
     }
     g_as_hist[iters < 63 ? iters : 63]++;

@@ -90,3 +90,24 @@ def test_merge_moments_is_running_mean_std():
         np.testing.assert_allclose(mean, rms.mean, rtol=1e-12)
         np.testing.assert_allclose(var, rms.var, rtol=1e-10)
         assert count == pytest.approx(rms.count)
+
+
+def test_speed_profile_and_oracle_speed_control():
+    """mimic_env.py:313-322 (profile), :406-408 (obs), :536-537 (deterministic init while following a profile)."""
+    from drloco_b200.walkers import speed_profile
+    from oracle.env_oracle import OracleMimicEnv
+    from oracle.physics import OraclePhysics
+    p = speed_profile([0.5, 1.0, 0.75], 4, 200)              # the reference docstring's example
+    assert p.shape == (800,) and p[0] == 0.5 and p[399] == 1.0 and p[400] == 1.0 and p[-1] == 0.75
+    assert np.allclose(np.diff(p[:400]), 0.5 / 399)
+    assert speed_profile([1.0, 1.0], 10, 200).shape == (2000,)          # defaults of activate_speed_control
+    assert speed_profile([0, 1, 2, 3], 1, 100).shape == (99,)           # int(100 / 3) = 33 per region
+    spec = make_spec(cfgm.EnvConfig())
+    env = OracleMimicEnv(spec, OraclePhysics(spec.model))
+    env.activate_speed_control([0.5, 1.0], 1)
+    obs = env.reset()
+    assert (env.refs.i_step, env.ep_dur) == (0, 0) and obs[1] == 0.5    # deterministic init: step 0 at 75 %
+    obs = env.step(np.zeros(8, np.float32))[0]
+    assert obs[1] == env.desired_walking_speed_trajectory[0]            # _get_obs runs before ep_dur += 1
+    obs = env.step(np.zeros(8, np.float32))[0]
+    assert obs[1] == env.desired_walking_speed_trajectory[1]

@@ -79,11 +79,26 @@ class PPO:
         self.policy = ActorCritic(self.D, self.A, self.cfg.hidden, self.cfg.init_logstd).to(self.device)
         self.opt = torch.optim.Adam(self.policy.parameters(), lr=self.cfg.lr_start, eps=1e-5)
         self.num_timesteps = 0
+        self.step_callback: Optional[Callable[[], object]] = None    # e.g. TrainingMonitor.on_step
         self.log: List[dict] = []
         dev, T, N = self.device, self.n_steps, self.N
         self.buf = dict(obs=torch.zeros(T, N, self.D, device=dev), act=torch.zeros(T, N, self.A, device=dev),
                         logp=torch.zeros(T, N, device=dev), val=torch.zeros(T, N, device=dev),
                         rew=torch.zeros(T, N, device=dev), done=torch.zeros(T, N, device=dev))
+
+    def save(self, path: str) -> None:
+        """checkpoint of the learner (policy, optimiser, step counter); the env statistics are saved by the env itself
+        (reference utils.save_model, utils.py:175-184, writes an SB3 zip + a pickled VecNormalize)."""
+        with open(path, "wb") as f:           # explicit handle: torch.save would otherwise rewrite the file suffix rules
+            torch.save({"policy": self.policy.state_dict(), "optimizer": self.opt.state_dict(),
+                        "num_timesteps": self.num_timesteps, "cfg": dataclasses.asdict(self.cfg)}, f)
+
+    def load(self, path: str) -> "PPO":
+        ck = torch.load(path, map_location=self.device, weights_only=False)
+        self.policy.load_state_dict(ck["policy"])
+        self.opt.load_state_dict(ck["optimizer"])
+        self.num_timesteps = int(ck["num_timesteps"])
+        return self
 
     def _lr(self) -> float:                                            # schedules.py:16-33 LinearDecay
         frac = min(1.0, self.num_timesteps / max(1, self.cfg.total_steps))
@@ -102,6 +117,8 @@ class PPO:
             nobs, rew, done = self.env.step_tensor(act.contiguous())
             b["rew"][t], b["done"][t] = rew, done.float()
             obs = nobs.clone()
+            if self.step_callback is not None:                       # SB3 BaseCallback._on_step cadence
+                self.step_callback()
         _, last_val = self.policy(obs)
         # GAE; SB3 1.0 does not bootstrap from the terminal observation
         adv = torch.zeros_like(b["rew"])
@@ -232,4 +249,6 @@ def evaluate_walking(policy: ActorCritic, train_env, n_episodes: int = 20, min_s
                 min_episode_duration=float(ep_len_h.min()),
                 mean_walking_speed=float((dist_h / (ep_len_h / spec.cfg.ctrl_freq)).mean()),
                 mean_reward_means=float((mean_rew.mean() - spec.cfg.alive_bonus) / spec.cfg.rew_scale),
-                count_stable_walks=max(reached, no_fall), n_episodes=n_episodes)
+                count_stable_walks=max(reached, no_fall), n_episodes=n_episodes,
+                # per-episode values, as TrainingMonitor.eval_walking collects them (callback.py:277,306-311)
+                moved_distances=dist_h.tolist(), ep_durs=ep_len_h.tolist(), mean_rewards=mean_rew.tolist())

@@ -546,17 +546,32 @@ def test_w165_config4_invariants():
     env.close()
 
 
-def test_ppo_consumer_runs_on_device_rollouts():
+def test_ppo_consumer_runs_on_device_rollouts(tmp_path):
     """next-tier smoke: the PPO loop (drloco_b200/ppo.py) consumes the tensor API end to end and produces finite updates."""
     from drloco_b200.ppo import PPO, PPOConfig, evaluate_walking
     from drloco_b200.vec_env import vec_env
     env = vec_env(W3D, num_envs=256, seed=1)
     cfg = PPOConfig(batch_size=256 * 16, minibatch_size=1024, total_steps=256 * 16 * 3)
-    agent = PPO(env, cfg, seed=0).learn(log_every=1)
+    from drloco_b200.training_monitor import TrainingMonitor
+    agent = PPO(env, cfg, seed=0)
+    mon = TrainingMonitor(agent, env.venv.cfg, str(tmp_path) + "/")     # callback.py: evaluation + logging cadence
+    mon.on_training_start()
+    agent.step_callback = mon.on_step
+    agent.learn(log_every=1)
+    mon.on_training_end()
     assert agent.num_timesteps == 256 * 16 * 3 and len(agent.log) == 3
+    assert mon.num_timesteps == agent.num_timesteps                      # one on_step per env.step
+    assert len(mon.moved_distances) == 10 and mon.min_episode_duration >= 1   # evaluated once (10 episodes < 1M steps)
+    assert mon.count_stable_walks == 0 and os.listdir(str(tmp_path) + "/models") == []   # untrained: checkpoint deleted
+    agent.save(str(tmp_path / "m.zip"))
+    w0 = agent.policy.action_net.weight.clone()
+    agent.policy.action_net.weight.data.zero_()
+    agent.load(str(tmp_path / "m.zip"))
+    assert torch.equal(agent.policy.action_net.weight, w0)
     for row in agent.log:
         assert all(np.isfinite(v) for v in row.values())
         assert 0.0 < row["mean_step_reward"] <= 1.2
     ev = evaluate_walking(agent.policy, env, n_episodes=4)
     assert ev["n_episodes"] == 4 and ev["min_episode_duration"] >= 1 and np.isfinite(ev["mean_walked_distance"])
+    assert len(ev["moved_distances"]) == len(ev["ep_durs"]) == len(ev["mean_rewards"]) == 4
     env.close()

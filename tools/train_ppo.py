@@ -25,6 +25,8 @@ def main():
     ap.add_argument("--minibatch", type=int, default=0)
     ap.add_argument("--out", default="gpurun_out/ppo_curve.json")
     ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--monitor", default="", help="directory: attach the TrainingMonitor (evaluation, checkpoints, "
+                                                  "scalars with the reference's tag names) and write there")
     args = ap.parse_args()
     env = vec_env("StraightMimicWalker", num_envs=args.envs, seed=33 + args.seed, norm_rew=True)
     cfg = PPOConfig(total_steps=args.steps)
@@ -37,8 +39,17 @@ def main():
     def cb(a, row):
         print(json.dumps({k: (round(v, 4) if isinstance(v, float) else v) for k, v in row.items()}), flush=True)
 
+    mon = None
+    if args.monitor:
+        from drloco_b200.training_monitor import TrainingMonitor
+        mon = TrainingMonitor(agent, env.venv.cfg, args.monitor.rstrip("/") + "/", verbose=1)
+        mon.on_training_start()
+        agent.step_callback = mon.on_step
     t0 = time.time()
     agent.learn(args.steps, log_every=5, callback=cb)
+    if mon:
+        mon.on_training_end()
+        print("checkpoints kept:", mon.saved, " steps to convergence:", mon.steps_to_convergence, flush=True)
     torch.cuda.synchronize()
     ev = evaluate_walking(agent.policy, env)
     print("evaluation (deterministic policy, 20 deterministic inits):", json.dumps(ev), flush=True)

@@ -528,51 +528,71 @@ class B200VecNormalize:
         return self.norm_obs_buf, self.norm_rew_buf, done
 
     # -- SB3 numpy API -----------------------------------------------------------------------------------
-    # float32 arrays are returned (SB3 converts observations to float32 tensors anyway); actions go through a pinned
-    # staging buffer, results come back with one asynchronous copy each and a single stream synchronisation.
+    # float32 arrays are returned (SB3 converts observations to float32 tensors anyway).  Actions go through a pinned
+    # staging buffer; obs / reward / done come back with one asynchronous copy each and ONE event wait; the terminal
+    # observations follow on a second event that is only waited for when an episode ended (their copy overlaps the
+    # host-side post-processing).  The returned observation array is a view of one of two alternating pinned buffers:
+    # it stays valid until the second following `step` (SB3's collect_rollouts reads `_last_obs` during the next step
+    # and stores it right after - that is covered); copy it to keep it longer.  `copy_outputs=True` restores copies.
+    copy_outputs = False
+
     def _host_buffers(self):
         if not hasattr(self, "_h"):
             N, D, A = self.num_envs, self._D, self.venv.act_dim
-            self._h = dict(act=torch.zeros(N, A).pin_memory(), obs=torch.zeros(N, D).pin_memory(),
+            self._h = dict(act=torch.zeros(N, A).pin_memory(),
+                           obs=[torch.zeros(N, D).pin_memory() for _ in range(2)],
                            rew=torch.zeros(N).pin_memory(), done=torch.zeros(N, dtype=torch.uint8).pin_memory(),
                            tobs=torch.zeros(N, D).pin_memory())
+            self._h_np = dict(act=self._h["act"].numpy(), obs=[t.numpy() for t in self._h["obs"]],
+                              rew=self._h["rew"].numpy(), done=self._h["done"].numpy(), tobs=self._h["tobs"].numpy())
+            self._hk = 0
             self._d_act = torch.zeros(N, A, device=self.device)
             self._d_ntobs = torch.zeros(N, D, device=self.device)
             self._no_info = [{} for _ in range(N)]
+            self._ev_out, self._ev_tobs = torch.cuda.Event(), torch.cuda.Event()
         return self._h
 
     def reset(self, inject=None):
         h = self._host_buffers()
-        h["obs"].copy_(self.reset_tensor(inject), non_blocking=True)
+        self._hk ^= 1
+        h["obs"][self._hk].copy_(self.reset_tensor(inject), non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()
-        return h["obs"].numpy().copy()
+        o = self._h_np["obs"][self._hk]
+        return o.copy() if self.copy_outputs else o
 
     def step_async(self, actions, inject=None):
         h = self._host_buffers()
-        h["act"].numpy()[...] = np.asarray(actions, np.float32).reshape(self.num_envs, -1)
+        self._h_np["act"][...] = np.asarray(actions, np.float32).reshape(self.num_envs, -1)
         self._d_act.copy_(h["act"], non_blocking=True)
         obs, rew, done = self.step_tensor(self._d_act, inject)
+        self._hk ^= 1
+        h["obs"][self._hk].copy_(obs, non_blocking=True)
+        h["rew"].copy_(rew, non_blocking=True)
+        h["done"].copy_(done, non_blocking=True)
+        stream = torch.cuda.current_stream(self.device)
+        self._ev_out.record(stream)
         with torch.cuda.device(self.device):
             lib.check(self._lib.drl_vecnorm_terminal(_ptr(self.venv.terminal_obs), _ptr(self._d_ntobs), _ptr(done),
                                                      self.num_envs, self._D, _ptr(self._rms[self._cur]),
                                                      float(self.clip_obs), float(self.epsilon), int(self.norm_obs),
                                                      self.venv._stream()), "drl_vecnorm_terminal")
         self.launches += 1
-        h["obs"].copy_(obs, non_blocking=True)
-        h["rew"].copy_(rew, non_blocking=True)
-        h["done"].copy_(done, non_blocking=True)
         h["tobs"].copy_(self._d_ntobs, non_blocking=True)
+        self._ev_tobs.record(stream)
 
     def step_wait(self):
-        h = self._h
-        torch.cuda.current_stream(self.device).synchronize()
-        done = h["done"].numpy().astype(bool)
+        hn = self._h_np
+        self._ev_out.synchronize()
+        done = hn["done"].astype(bool)
         infos = list(self._no_info)
-        if done.any():
-            tobs = h["tobs"].numpy()
-            for i in np.nonzero(done)[0]:
-                infos[i] = {"terminal_observation": tobs[i].copy()}
-        return h["obs"].numpy().copy(), h["rew"].numpy().copy(), done, infos
+        idx = np.flatnonzero(done)
+        if idx.size:
+            self._ev_tobs.synchronize()
+            rows = hn["tobs"][idx]                       # one gather = fresh memory for all terminal observations
+            for k, i in enumerate(idx.tolist()):
+                infos[i] = {"terminal_observation": rows[k]}
+        obs = hn["obs"][self._hk]
+        return (obs.copy() if self.copy_outputs else obs), hn["rew"].copy(), done, infos
 
     def step(self, actions, inject=None):
         self.step_async(actions, inject)

@@ -29,6 +29,8 @@ REPO = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, REPO)
 
 ENV_ID = "StraightMimicWalker"
+W3D_WORKLOAD = ("MimicWalker3d straight walking, %d batched envs per GPU, random-action step+reward throughput "
+                "(BASELINE.json configs[1])")
 ENVS_PER_GPU = 4096
 ALGO_BYTES_PER_ENV_STEP = 425.0        # SURVEY.md §8d / DESIGN.md
 ALGO_FLOP_PER_ENV_STEP = 0.32e6        # 16 kFLOP per dynamics evaluation x 20 evaluations (W3D, RK4)
@@ -172,8 +174,10 @@ def run_reference(args, emit):
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": t_total / max(1, args.steps) * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic random actions on the shipped straight-walking mocap",
-            "config": {"workload": "MimicWalker3d straight walking, random-action step+reward throughput",
-                       "envs": cores * per_proc_envs, "integrator": "rk4"},
+            # the same workload as the CUDA arm's line (its `config`), measured on a bounded sample of it
+            "config": {"workload": W3D_WORKLOAD % args.envs_per_gpu, "envs_per_gpu": args.envs_per_gpu,
+                       "integrator": "rk4", "frame_skip": 5, "parallelism": f"{cores} host processes (SubprocVecEnv-like)",
+                       "sample_envs": cores * per_proc_envs},
             "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -327,8 +331,7 @@ def main():
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic random actions U(-1,1) on the shipped straight-walking mocap, random-init (RSI) states",
-            "config": {"workload": ("MimicWalker3d straight walking, %d batched envs per GPU, random-action step+reward "
-                                    "throughput (BASELINE.json configs[1])" % n) if args.env_id == ENV_ID else
+            "config": {"workload": (W3D_WORKLOAD % n) if args.env_id == ENV_ID else
                                    ("MimicWalker165cm65kg on the synthetic loco3d mocap, %d envs per GPU, RSI + early "
                                     "termination (BASELINE.json configs[3])" % n),
                        "envs_per_gpu": n, "integrator": args.integrator, "frame_skip": env.spec.frame_skip,

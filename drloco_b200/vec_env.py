@@ -634,11 +634,25 @@ class B200VecNormalize:
         with open(path, "wb") as f:
             pickle.dump(self.state_dict(), f)
 
+    def save_sb3(self, path: str) -> None:
+        """the same statistics as a pickle under SB3's class names (utils.py:183-184 writes such a file); see
+        drloco_b200/checkpoint.py for what was and was not verified."""
+        from .checkpoint import write_sb3_vecnormalize
+        write_sb3_vecnormalize(path, {**self.state_dict(), "training": self.training}, self.num_envs)
+
     @staticmethod
     def load(path: str, venv: B200MimicVecEnv) -> "B200VecNormalize":
+        """accepts this class's own file and a pickled SB3 ``VecNormalize`` (``envs/env_<ckpt>`` of the reference)."""
         import pickle
-        with open(path, "rb") as f:
-            sd = pickle.load(f)
+        sd = None
+        try:
+            with open(path, "rb") as f:
+                sd = pickle.load(f)
+        except (ImportError, AttributeError):        # SB3 / gym classes named by the pickle are not importable here
+            pass
+        if not isinstance(sd, dict):
+            from .checkpoint import read_sb3_vecnormalize
+            sd = read_sb3_vecnormalize(path)
         vn = B200VecNormalize(venv)
         vn.load_state_dict(sd)
         return vn

@@ -37,7 +37,7 @@ def test_sharded_moments_match_single_process():
     from oracle.env_oracle import RunningMeanStd
     total, d, world = 37, 6, 2
     port = _free_port()
-    mgr = mp.Manager()
+    mgr = mp.get_context("spawn").Manager()        # not fork: the pytest process is multi-threaded once torch is loaded
     out = mgr.dict()
     mp.spawn(_worker, args=(world, port, total, d, out), nprocs=world, join=True)
     rng = np.random.default_rng(123)

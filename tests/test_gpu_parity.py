@@ -440,8 +440,16 @@ def test_vec_env_factory_save_load(tmp_path):
     o = env2.reset()
     assert o.shape == (1, 29) and np.isfinite(o).all() and np.abs(o).max() <= 10.0
     assert env.get_attr("ep_len_smoothed") == env.venv.get_attr("ep_len_smoothed")
+    # the same statistics in the reference's own file format (pickled SB3 VecNormalize, utils.py:183-184) and back
+    path_sb3 = str(tmp_path / "env_ckpt_sb3")
+    env.save_sb3(path_sb3)
+    env3 = vec_env(W3D, num_envs=2, seed=3, norm_rew=False, load_path=path_sb3)
+    np.testing.assert_array_equal(env3.obs_rms.mean, env.obs_rms.mean)
+    np.testing.assert_array_equal(env3.obs_rms.var, env.obs_rms.var)
+    assert env3.obs_rms.count == env.obs_rms.count and env3.ret_rms.var == env.ret_rms.var
     env.close()
     env2.close()
+    env3.close()
 
 
 # --------------------------------------------------------------------------------------------------------------------

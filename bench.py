@@ -346,7 +346,7 @@ def main():
             "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
                          "frac": achieved_gbs / hbm_peak,
                          # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full (profiles/r01_step_kernel_final.md)
-                         "traffic": 2758144 if (args.env_id == ENV_ID and n == 4096) else None, "peak_source": which,
+                         "traffic": 2836736 if (args.env_id == ENV_ID and n == 4096) else None, "peak_source": which,
                          "kernel": "mimic_step_kernel", "kernel_ms": kernel_ms,
                          "note": "latency/FP32-bound by construction: %d algorithmic bytes per env-step" % algo_bytes},
             "fp32": {"achieved_tflops": achieved_tf, "peak_tflops": fp32_peak,

@@ -100,6 +100,42 @@ extern "C" int drl_destroy(DrlEnv* e) {
   return DRL_OK;
 }
 
+// persistent per-env state; on failure the caller releases whatever was allocated (free_state)
+static int alloc_state(DrlEnv* e, size_t N) {
+  CUDA_TRY(cudaMalloc(&e->d_model, sizeof(DevModel)));
+  CUDA_TRY(cudaMalloc(&e->state_f, N * 4 * e->G * sizeof(float)));
+  CUDA_TRY(cudaMalloc(&e->state_i, N * kCurCount8 * sizeof(int)));
+  CUDA_TRY(cudaMalloc(&e->state_as, N * e->G * sizeof(int)));
+  CUDA_TRY(cudaMemset(e->state_as, 0, N * e->G * sizeof(int)));
+  CUDA_TRY(cudaMalloc(&e->state_d, N * 4 * sizeof(double)));
+  CUDA_TRY(cudaMalloc(&e->extras_last, N * 16 * sizeof(float)));
+  CUDA_TRY(cudaMalloc(&e->stats, DRL_STATS_COUNT * sizeof(double)));
+  CUDA_TRY(cudaMalloc(&e->ring_len, e->ring_cap * sizeof(int)));
+  CUDA_TRY(cudaMalloc(&e->ring_ret, e->ring_cap * sizeof(float)));
+  CUDA_TRY(cudaMalloc(&e->ring_head, sizeof(unsigned long long)));
+  CUDA_TRY(cudaMemset(e->state_f, 0, N * 4 * e->G * sizeof(float)));
+  CUDA_TRY(cudaMemset(e->state_i, 0, N * kCurCount8 * sizeof(int)));
+  CUDA_TRY(cudaMemset(e->state_d, 0, N * 4 * sizeof(double)));
+  CUDA_TRY(cudaMemset(e->extras_last, 0, N * 16 * sizeof(float)));
+  CUDA_TRY(cudaMemset(e->stats, 0, DRL_STATS_COUNT * sizeof(double)));
+  CUDA_TRY(cudaMemset(e->ring_head, 0, sizeof(unsigned long long)));
+  // count_steps_same_vel starts at 1 (straight_walk_trajecs.py:124)
+  std::vector<int> init(N * kCurCount8, 0);
+  for (size_t i = 0; i < N; i++) init[i * kCurCount8 + kCurCount] = 1;
+  CUDA_TRY(cudaMemcpy(e->state_i, init.data(), init.size() * sizeof(int), cudaMemcpyHostToDevice));
+  return DRL_OK;
+}
+
+static void free_state(DrlEnv* e) {
+  void** ptrs[] = {(void**)&e->d_model, (void**)&e->state_f, (void**)&e->state_i, (void**)&e->state_as,
+                   (void**)&e->state_d, (void**)&e->extras_last, (void**)&e->stats, (void**)&e->ring_len,
+                   (void**)&e->ring_ret, (void**)&e->ring_head};
+  for (void** p : ptrs) {
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+  }
+}
+
 static bool supports(const DrlWalkerModel* m, int j, int b) {
   const int jb = m->dof_body[j];
   while (b >= 0) {
@@ -293,27 +329,12 @@ extern "C" int drl_upload_model(DrlEnv* e, const DrlWalkerModel* m) {
   CUDA_TRY(cudaSetDevice(c.device));
   const size_t N = (size_t)c.num_envs;
   if (!e->d_model) {
-    CUDA_TRY(cudaMalloc(&e->d_model, sizeof(DevModel)));
-    CUDA_TRY(cudaMalloc(&e->state_f, N * 4 * e->G * sizeof(float)));
-    CUDA_TRY(cudaMalloc(&e->state_i, N * kCurCount8 * sizeof(int)));
-    CUDA_TRY(cudaMalloc(&e->state_as, N * e->G * sizeof(int)));
-    CUDA_TRY(cudaMemset(e->state_as, 0, N * e->G * sizeof(int)));
-    CUDA_TRY(cudaMalloc(&e->state_d, N * 4 * sizeof(double)));
-    CUDA_TRY(cudaMalloc(&e->extras_last, N * 16 * sizeof(float)));
-    CUDA_TRY(cudaMalloc(&e->stats, DRL_STATS_COUNT * sizeof(double)));
-    CUDA_TRY(cudaMalloc(&e->ring_len, e->ring_cap * sizeof(int)));
-    CUDA_TRY(cudaMalloc(&e->ring_ret, e->ring_cap * sizeof(float)));
-    CUDA_TRY(cudaMalloc(&e->ring_head, sizeof(unsigned long long)));
-    CUDA_TRY(cudaMemset(e->state_f, 0, N * 4 * e->G * sizeof(float)));
-    CUDA_TRY(cudaMemset(e->state_i, 0, N * kCurCount8 * sizeof(int)));
-    CUDA_TRY(cudaMemset(e->state_d, 0, N * 4 * sizeof(double)));
-    CUDA_TRY(cudaMemset(e->extras_last, 0, N * 16 * sizeof(float)));
-    CUDA_TRY(cudaMemset(e->stats, 0, DRL_STATS_COUNT * sizeof(double)));
-    CUDA_TRY(cudaMemset(e->ring_head, 0, sizeof(unsigned long long)));
-    // count_steps_same_vel starts at 1 (straight_walk_trajecs.py:124)
-    std::vector<int> init(N * kCurCount8, 0);
-    for (size_t i = 0; i < N; i++) init[i * kCurCount8 + kCurCount] = 1;
-    CUDA_TRY(cudaMemcpy(e->state_i, init.data(), init.size() * sizeof(int), cudaMemcpyHostToDevice));
+    const int rc = alloc_state(e, N);
+    if (rc != DRL_OK) {          // e.g. out of memory for a very large batch: leave the env without a model
+      free_state(e);
+      (void)cudaGetLastError();   // a failed cudaMalloc also parks its code as the "last error": clear it
+      return rc;
+    }
   }
   e->have_model = true;
   if (e->have_mocap) CUDA_TRY(cudaMemcpy(e->d_model, &e->hm, sizeof(DevModel), cudaMemcpyHostToDevice));

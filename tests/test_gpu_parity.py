@@ -503,6 +503,21 @@ def test_c_abi_call_order_errors():
     cm.nv = 15
     assert l.drl_upload_model(h, C.byref(cm)) == -4                          # DRL_ERR_UNSUPPORTED
     assert l.drl_destroy(h) == 0
+    # a batch whose state cannot be allocated (2^31-1 envs x 256 B of state rows > HBM): a clean error, nothing leaked,
+    # and the library keeps working afterwards
+    free0 = torch.cuda.mem_get_info()[0]
+    cfg.num_envs = 2 ** 31 - 1
+    h2 = C.c_void_p()
+    assert l.drl_create(C.byref(cfg), C.byref(h2)) == 0
+    cm = cabi.pack_model(spec.model)
+    assert l.drl_upload_model(h2, C.byref(cm)) == -2                         # DRL_ERR_CUDA
+    assert b"memory" in l.drl_last_error().lower()
+    assert l.drl_step(h2, p, p, p, p, None, None, None, None) == -3          # still "nothing uploaded"
+    assert l.drl_destroy(h2) == 0
+    assert torch.cuda.mem_get_info()[0] >= free0 - (64 << 20)
+    env = _env(W3D, 8)
+    env.reset()
+    env.close()
 
 
 def test_odd_env_count_and_masked_reset():

@@ -20,8 +20,8 @@ EXTRA_NAMES = ("pos_rew", "vel_rew", "com_rew", "walked_distance", "mean_abs_tor
 EXTRA_COUNT = 16
 STAT_NAMES = ("episodes", "ep_len_sum", "ep_ret_sum", "ep_mean_rew_sum", "pos_rew_sum", "vel_rew_sum", "com_rew_sum",
               "rew_steps", "moved_distance_sum", "abs_torque_sum", "env_steps", "blowups", "falls", "timeouts",
-              "solver_iters", "dyn_evals", "solver_capped")
-STATS_COUNT = 17
+              "solver_iters", "dyn_evals", "solver_capped", "et_com_low", "et_trunk", "et_drunk")
+STATS_COUNT = 20
 
 d, i32 = C.c_double, C.c_int32
 
@@ -56,7 +56,7 @@ class DrlConfig(C.Structure):
         ("obs_dim", i32), ("act_dim", i32),
         ("mirror_obs_idx", i32 * MAX_OBS), ("mirror_obs_sign", C.c_float * MAX_OBS),
         ("mirror_act_idx", i32 * MAX_ACT), ("mirror_act_sign", C.c_float * MAX_ACT),
-        ("lanes_per_env", i32),
+        ("lanes_per_env", i32), ("early_termination", i32),
     ]
 
 

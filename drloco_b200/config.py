@@ -35,6 +35,8 @@ class EnvConfig:
     alive_bonus: float = 0.2                            # hypers.py:55 (0.2 * rew_scale)
     ep_dur_max: int = 3000                              # hypers.py:58
     fall_z: float = 0.5                                 # mimic_env.py:120
+    early_termination: bool = False                     # True: do_terminate_early (mimic_env.py:652-702) also ends the
+                                                        # episode; the reference never does (mimic_env.py:120-123)
     gamma: float = 0.0                                  # 0 -> by ctrl_freq, hypers.py:68
     integrator: str = "rk4"                             # xml:11; "euler" = MuJoCo semi-implicit Euler (fast mode)
     seed: int = 33                                      # utils.py:97

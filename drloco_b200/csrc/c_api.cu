@@ -322,6 +322,8 @@ extern "C" int drl_upload_model(DrlEnv* e, const DrlWalkerModel* m) {
   }
   d.com_mask = 0x7u;     // _get_COM_indices() == [0,1,2] for both walkers
   d.com_z_dof = 2;
+  d.early_termination = c.early_termination ? 1 : 0;
+  d.trunk_dof0 = 3;      // _get_trunk_rot_joint_indices() == [3,4,5] for both walkers (frontal, sagittal, axial)
   d.seed = c.seed; d.env_id_offset = c.env_id_offset;
   e->nv = m->nv;
   e->G = G;

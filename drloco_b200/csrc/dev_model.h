@@ -61,6 +61,7 @@ struct alignas(16) DevModel {
   unsigned box_body_mask;            // bodies that carry a box geom (their contact accumulators are segment-written)
   unsigned com_mask;                 // dofs excluded from the pose / velocity reward (COM indices 0,1,2)
   int com_z_dof;
+  int early_termination, trunk_dof0, pad_et[2];   // do_terminate_early: off/on, first of the three trunk rotation dofs
   // ---- mocap ----
   int cursor_mode, increment, n_steps, n_samples, com_z_col, des_vel_window;
   unsigned long long seed;

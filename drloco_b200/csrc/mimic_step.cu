@@ -1060,10 +1060,23 @@ __global__ void __launch_bounds__(128, 4) mimic_step_kernel(const StepArgs A, co
   }
   const float comz = __shfl_sync(kFull, q, M.com_z_dof, G);
   const bool timeout = c.ep_dur >= M.ep_dur_max;
-  done = (comz < M.fall_z) || timeout;                          // mimic_env.py:113-120
+  float rq, rv;
+  ref_lookup(M, A, c, dist, zoff, l, G, L.isdof, rq, rv);
+  // do_terminate_early (mimic_env.py:652-702, 3D branch): the reference computes nothing from it in step(); here the
+  // reasons are counted and, when configured, end the episode
+  bool et_low, et_trunk, et_drunk;
   {
-    float rq, rv;
-    ref_lookup(M, A, c, dist, zoff, l, G, L.isdof, rq, rv);
+    const int t0 = M.trunk_dof0;
+    const float front_dev = fabsf(__shfl_sync(kFull, q - rq, t0, G));
+    const float sag = __shfl_sync(kFull, q, t0 + 1, G), comy = __shfl_sync(kFull, q, 1, G);
+    et_low = comz < 0.75f;
+    et_trunk = (sag > 0.3f || sag < -0.05f) || front_dev > 0.2f;
+    et_drunk = fabsf(comy) > 0.2f;
+    if (A.playback) et_low = et_trunk = et_drunk = false;
+  }
+  const bool et_done = M.early_termination && (et_low || et_trunk || et_drunk);
+  done = (comz < M.fall_z) || timeout || et_done;               // mimic_env.py:113-120
+  {
     const float dq = L.isdof ? q - rq : 0.f, dv = L.isdof ? v - rv : 0.f;
     const bool iscom = (M.com_mask >> l) & 1u;
     const float sp = group_sum<G>(iscom ? 0.f : dq * dq);
@@ -1105,6 +1118,11 @@ __global__ void __launch_bounds__(128, 4) mimic_step_kernel(const StepArgs A, co
     atomicAdd(&A.stats[DRL_STAT_SOLVER_ITERS], (double)cnt.iters);
     atomicAdd(&A.stats[DRL_STAT_DYN_EVALS], (double)cnt.evals);
     if (cnt.capped) atomicAdd(&A.stats[DRL_STAT_SOLVER_CAPPED], (double)cnt.capped);
+    if (!bad) {
+      if (et_low) atomicAdd(&A.stats[DRL_STAT_ET_COM_LOW], 1.0);
+      if (et_trunk) atomicAdd(&A.stats[DRL_STAT_ET_TRUNK], 1.0);
+      if (et_drunk) atomicAdd(&A.stats[DRL_STAT_ET_DRUNK], 1.0);
+    }
     if (A.extras) {
       float* ex = A.extras + (size_t)env * 16;
       ex[0] = pos_rew; ex[1] = vel_rew; ex[2] = com_rew; ex[3] = walked; ex[4] = mean_abs_torque;

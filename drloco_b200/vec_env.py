@@ -122,6 +122,7 @@ class B200MimicVecEnv:
         for i in range(s.act_dim):
             c.mirror_act_idx[i], c.mirror_act_sign[i] = int(ai[i]), float(asn[i])
         c.lanes_per_env = lanes_per_env
+        c.early_termination = int(bool(cfg.early_termination))
         return c
 
     def _upload_mocap(self):

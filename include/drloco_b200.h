@@ -111,6 +111,10 @@ typedef struct {
   int32_t mirror_act_idx[DRL_MAX_ACT];
   float mirror_act_sign[DRL_MAX_ACT];
   int32_t lanes_per_env;         /* 0 = choose from num_envs; else 16 or 32 */
+  int32_t early_termination;     /* MimicEnv.do_terminate_early (mimic_env.py:652-702).  The reference defines the check
+                                  * but never lets it end an episode (mimic_env.py:120-123): 0 = same here, the three
+                                  * reasons are only counted (DRL_STAT_ET_*); 1 = a firing check also sets done (the
+                                  * terminal reward is then -0.0 like a fall). */
 } DrlConfig;
 
 typedef struct DrlEnv DrlEnv;    /* opaque: persistent per-env state, mocap tables, RNG counters */
@@ -182,7 +186,9 @@ typedef enum {
   DRL_STAT_ENV_STEPS = 10, DRL_STAT_BLOWUPS = 11, DRL_STAT_FALLS = 12, DRL_STAT_TIMEOUTS = 13,
   DRL_STAT_SOLVER_ITERS = 14, DRL_STAT_DYN_EVALS = 15,
   DRL_STAT_SOLVER_CAPPED = 16,   /* evaluations whose active-set iteration stopped at the cap instead of converging */
-  DRL_STATS_COUNT = 17
+  /* env-steps on which do_terminate_early's reasons held: COM-Z < 0.75 / trunk angle out of range / |COM-Y| > 0.2 */
+  DRL_STAT_ET_COM_LOW = 17, DRL_STAT_ET_TRUNK = 18, DRL_STAT_ET_DRUNK = 19,
+  DRL_STATS_COUNT = 20
 } DrlStat;
 int drl_get_stats(DrlEnv* env, double* stats, void* stream);
 int drl_reset_stats(DrlEnv* env, void* stream);

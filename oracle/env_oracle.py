@@ -247,8 +247,23 @@ class OracleMimicEnv:
         self.walked_distance += float(np.linalg.norm(vel_vec)) * 1 / self.cfg.ctrl_freq
         com_z = self.qpos[self.spec.com_indices[-1]]
         done = bool(com_z < self.cfg.fall_z or self.ep_dur >= self.cfg.ep_dur_max)
+        self.et_flags = self.do_terminate_early()            # mimic_env.py:122-123 (commented out in the reference)
+        if self.cfg.early_termination and self.et_flags[0]:
+            done = True
         reward = self._get_ET_reward() if done else self.get_imitation_reward() + self.cfg.alive_bonus
         return obs, reward, done, {}
+
+    def do_terminate_early(self):                            # mimic_env.py:652-702 (3D branch: trunk dofs 3,4,5)
+        if self._PLAYBACK_REF_TRAJECS:
+            return [False] * 4
+        qpos, ref = self.qpos, self.refs.get_qpos()
+        com_height, com_y = qpos[2], qpos[1]
+        front, sag, _ = qpos[3:6]
+        front_dev = abs(qpos[3] - ref[3])
+        trunk = bool((sag > 0.3 or sag < -0.05) or front_dev > 0.2)
+        drunk = bool(abs(com_y) > 0.2)
+        low = bool(com_height < 0.75)
+        return [low or trunk or drunk, low, trunk, drunk]
 
     def reset(self, i_step=None, pos=None):                  # MujocoEnv.reset + mimic_env.py:526-572
         self.ep_dur = 0

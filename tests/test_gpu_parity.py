@@ -286,6 +286,62 @@ def test_blowup_path_and_eval_mode():
     env.close()
 
 
+@pytest.mark.parametrize("enabled", [False, True])
+def test_early_termination_check(enabled):
+    """do_terminate_early (mimic_env.py:652-702): reasons counted always; ends the episode only when configured
+    (the reference never lets it, mimic_env.py:120-123)."""
+    from drloco_b200.vec_env import B200MimicVecEnv
+    n, steps = 32, 40
+    cfg = EnvConfig(env_id=W3D, early_termination=enabled)
+    env = B200MimicVecEnv(W3D, num_envs=n, cfg=cfg, seed=5)
+    spec = env.spec
+    env.debug_set(frame_skip_override=0)
+    ora = _oracle(spec, n, physics=lambda: _FrozenPhysics(spec.model))
+    rng = np.random.default_rng(8)
+    istep, pos = _rsi(spec, n, rng)
+    env.reset(inject=(istep, pos)), ora.reset(istep, pos)
+    env.reset_stats()
+    want = np.zeros(3)
+    n_done = 0
+    for k in range(steps):
+        qg, vg, cg = env.get_state()
+        q_new = qg.copy()
+        # push single quantities over their thresholds: COM-Y, COM-Z (between 0.5 and 0.75), frontal and sagittal trunk angle
+        who = rng.integers(0, 6, n)
+        q_new[who == 1, 1] = rng.choice([-0.25, 0.25])
+        q_new[who == 2, 2] = 0.7
+        q_new[who == 3, 3] += 0.3
+        q_new[who == 4, 4] = rng.choice([-0.1, 0.35])
+        env.set_state(q_new, vg, cg)
+        for i, e in enumerate(ora.envs):
+            e.env.qpos[:] = q_new[i].astype(np.float64)
+            e.env.qvel[:] = vg[i].astype(np.float64)
+        a = rng.uniform(-1, 1, (n, 8)).astype(np.float32)
+        og, rg, dg, _ = env.step(a, inject=(istep, pos))
+        flags = []
+        oo, ro, do = [], [], []
+        for i, m in enumerate(ora.envs):                     # flags must be read before the auto-reset of OracleVecEnv
+            o, r, d, _ = m.step(a[i])
+            flags.append(m.env.et_flags)
+            if d:
+                o = m.env.reset(istep[i], pos[i])
+            oo.append(o), ro.append(r), do.append(d)
+        flags, do = np.array(flags), np.array(do)
+        want += flags[:, 1:].sum(axis=0)
+        np.testing.assert_array_equal(dg, do)
+        assert _rel(og, np.stack(oo)) < 2e-5 and np.abs(rg - np.array(ro)).max() < 2e-5
+        np.testing.assert_array_equal(np.signbit(rg), np.signbit(np.array(ro)))
+        if enabled:
+            np.testing.assert_array_equal(dg, flags[:, 0])   # nothing falls below 0.5 or times out in this test
+        else:
+            assert not dg.any()
+        n_done += int(dg.sum())
+    st = env.stats()
+    assert [st["et_com_low"], st["et_trunk"], st["et_drunk"]] == want.tolist() and want.min() > 10
+    assert st["falls"] == n_done and (n_done > 50 if enabled else n_done == 0)
+    env.close()
+
+
 def test_speed_control_profile():
     """env_method('activate_speed_control') (mimic_env.py:298-327,406-408,536-537): the desired-velocity observation
     follows the profile indexed by the episode duration, resets become deterministic."""

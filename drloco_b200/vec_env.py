@@ -671,6 +671,9 @@ class B200VecNormalize:
     def seed(self, seed=None):
         return self.venv.seed(seed)
 
+    def env_is_wrapped(self, wrapper_class, indices=None):
+        return self.venv.env_is_wrapped(wrapper_class, indices)
+
     def close(self):
         self.venv.close()
 

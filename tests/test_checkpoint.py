@@ -52,8 +52,12 @@ def test_policy_key_mapping_round_trip(tmp_path):
         assert sorted(inner) == sorted(sd)
     pol2 = ActorCritic(29, 8)
     assert ck.load_sb3_zip(path, pol2) == {"gamma": 0.995}
+    for (k1, v1), (k2, v2) in zip(pol.state_dict().items(), pol2.state_dict().items()):
+        assert k1 == k2 and torch.equal(v1, v2)                           # parameters are bit-identical
     x = torch.randn(5, 29)
-    assert torch.equal(pol2(x)[0], pol(x)[0]) and torch.equal(pol2(x)[1], pol(x)[1])
+    # outputs only to rounding: CPU GEMM blocking may depend on the buffers' alignment
+    assert torch.allclose(pol2(x)[0], pol(x)[0], rtol=1e-5, atol=1e-6)
+    assert torch.allclose(pol2(x)[1], pol(x)[1], rtol=1e-5, atol=1e-5)
 
 
 def _pickle_sb3_like_vecnormalize(path, D=29):

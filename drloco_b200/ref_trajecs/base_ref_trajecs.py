@@ -41,6 +41,8 @@ class MocapTables:
     com_z_col: int                 # column of ``ref`` holding the COM-Z position (straight:482, loco3d:48)
     des_vel_prefix: Optional[np.ndarray] = None   # float64 [n_samples+1, 2] prefix sums for loco3d:51-68
     des_vel_window: int = 0
+    des_vel_rows: Optional[np.ndarray] = None     # float64 [2, n_samples] the velocity rows themselves (the oracle
+                                                  # takes np.mean of the slice exactly like loco3d:62-68)
 
     @property
     def n_steps(self) -> int:

@@ -94,4 +94,5 @@ class Loco3dReferenceTrajectories(BaseReferenceTrajectories):
         return MocapTables(cursor_mode=CURSOR_WRAP, increment=self._increment, ref=ref,
                            step_off=np.zeros(1, np.int32), step_len=np.array([T], np.int32),
                            left_step=np.zeros(1, np.uint8), step_vel=np.zeros(1), step_last_comx=np.zeros(1),
-                           com_z_col=self._qpos_indices.index(PELVIS_TY), des_vel_prefix=pre, des_vel_window=window)
+                           com_z_col=self._qpos_indices.index(PELVIS_TY), des_vel_prefix=pre, des_vel_window=window,
+                           des_vel_rows=np.stack([self._qvel_full[PELVIS_TX], self._qvel_full[PELVIS_TZ]]))

@@ -72,8 +72,8 @@ class RefCursor:
         n = end - self.pos
         if n <= 0:
             return [math.nan, math.nan]                     # mean of an empty slice (Q23)
-        pre = self.t.des_vel_prefix
-        return [float((pre[end, 0] - pre[self.pos, 0]) / n), float((pre[end, 1] - pre[self.pos, 1]) / n)]
+        rows = self.t.des_vel_rows                          # np.mean of the slice, as the reference computes it
+        return [np.mean(rows[0, self.pos:end]), np.mean(rows[1, self.pos:end])]
 
     # -- motion ---------------------------------------------------------------------------------
     def next(self):
@@ -201,7 +201,7 @@ class OracleMimicEnv:
         out = []
         for j in self.spec.phase_joints:
             pos, vel = self.qpos[j], self.qvel[j]
-            out += [math.atan2(vel, -pos) / math.pi, math.sqrt(pos * pos + vel * vel) / 5]
+            out += [np.arctan2(vel, -pos) / np.pi, np.linalg.norm([pos, vel]) / 5]
         return out
 
     def activate_speed_control(self, speeds=(1.0, 1.0), speed_profile_duration=10):   # mimic_env.py:298-322

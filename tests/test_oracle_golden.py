@@ -74,3 +74,41 @@ def test_rollout_matches_reference(spec, golden_dir):
         got = np.array([float(getattr(m, name)) for m in venv.envs])
         np.testing.assert_allclose(got, g["mon_" + name], rtol=1e-12, atol=0, err_msg=name)
     np.testing.assert_array_equal([x for m in venv.envs for x in m.ep_lens], g["mon_ep_lens_flat"])
+
+
+def test_w165_rollout_matches_reference(golden_dir):
+    """reference MimicWalker165cm65kgEnv + Monitor (wrap cursor base:95-103, joint-phase estimates mimic_env.py:330-360,
+    2-D desired velocity loco3d:51-68, no mirroring) over the oracle physics vs OracleVecEnv, same actions / RSI draws.
+    The recording is synthetic_loco3d(seed 0) on both sides (the reference read it from a .mat with its own schema)."""
+    from drloco_b200.config import EnvConfig
+    g = np.load(os.path.join(golden_dir, "w165_rollout.npz"))
+    spec = make_spec(EnvConfig(env_id="MimicWalker165cm65kg"))
+    T, N = g["actions"].shape[:2]
+    assert spec.obs_dim == g["obs"].shape[2] == 47 and spec.act_dim == 13
+    venv = OracleVecEnv(spec, N, lambda: OraclePhysics(spec.model))
+    zeros = np.zeros(N, np.int32)
+    obs = venv.reset(zeros, g["rsi"][0])
+    np.testing.assert_array_equal(obs, g["obs0"])
+    np.testing.assert_array_equal(np.stack([e.env.qpos for e in venv.envs]), g["qpos0"])
+    np.testing.assert_array_equal([[e.env.refs.pos, e.env.ep_dur] for e in venv.envs], g["cursor0"])
+    wraps = 0
+    for t in range(T):
+        before = np.array([e.env.refs.pos for e in venv.envs])
+        obs, rew, done, infos = venv.step(g["actions"][t], zeros, g["rsi"][t + 1])
+        np.testing.assert_array_equal(done.astype(np.uint8), g["done"][t], err_msg=f"t={t}")
+        np.testing.assert_array_equal(rew, g["rew"][t], err_msg=f"t={t}")
+        assert np.array_equal(np.signbit(rew), np.signbit(g["rew"][t]))
+        np.testing.assert_array_equal(obs, g["obs"][t], err_msg=f"t={t}")
+        for i in range(N):
+            if done[i]:
+                np.testing.assert_array_equal(infos[i]["terminal_observation"], g["terminal_obs"][t, i])
+            else:
+                assert (venv.envs[i].env.refs.pos, venv.envs[i].env.ep_dur) == tuple(g["cursor"][t, i])
+                wraps += int(venv.envs[i].env.refs.pos < before[i])
+    assert wraps >= 2 and g["done"].sum() >= 5             # the fixture crosses the end of the recording and has resets
+    for name in ("ep_len_smoothed", "ep_ret_smoothed", "mean_reward_smoothed", "moved_distance",
+                 "mean_ep_pos_rew_smoothed", "mean_ep_vel_rew_smoothed", "mean_ep_com_rew_smoothed",
+                 "mean_abs_ep_torque_smoothed"):
+        got = np.array([float(getattr(m, name)) for m in venv.envs])
+        np.testing.assert_allclose(got, g["mon_" + name], rtol=1e-12, atol=0, err_msg=name)
+    np.testing.assert_array_equal([x for m in venv.envs for x in m.ep_lens], g["mon_ep_lens_flat"])

@@ -17,6 +17,7 @@ Conditions of the run (recorded in the fixture):
     observation and reset.
 
 Usage: python tools/gen_golden.py            (writes tests/golden/w3d_rollout.npz, w3d_cursor.npz)
+       python tools/gen_golden.py w165       (writes tests/golden/w165_rollout.npz; own process: other ENV_ID)
 """
 import collections
 import collections.abc
@@ -212,6 +213,142 @@ def load_reference():
     return MimicWalker3dEnv, Monitor, utils
 
 
+def _load_module_with(name, rel_path, replacements):
+    """exec a reference module from source with textual substitutions and register it (also on its package)."""
+    path = os.path.join(REF, rel_path)
+    src = open(path).read()
+    for a, b in replacements:
+        assert a in src, (rel_path, a)
+        src = src.replace(a, b)
+    mod = types.ModuleType(name)
+    mod.__file__ = path
+    sys.modules[name] = mod
+    exec(compile(src, path, "exec"), mod.__dict__)
+    pkg, _, leaf = name.rpartition(".")
+    setattr(sys.modules[pkg], leaf, mod)
+    return mod
+
+
+def load_reference_w165(project_dir):
+    """The reference configured for MimicWalker165cm65kg.  Substitutions, all of them settings the reference expects its
+    user to edit: ENV_ID (config.py:18), policy mirroring off (hypers.py:23,31-39: "only works with the Straight
+    Walker"), and the project path the loco3d loader reads its (missing) .mat from."""
+    sys.path.insert(0, REF)
+    work = os.path.join(tempfile.mkdtemp(), "code", "torch")
+    os.makedirs(work)
+    os.chdir(work)
+    import torch  # noqa: F401
+    install_stubs()
+    import drloco.config  # noqa: F401
+    _load_module_with("drloco.config.config", "drloco/config/config.py",
+                      [("ENV_ID = 'StraightMimicWalker'", "ENV_ID = 'MimicWalker165cm65kg'")])
+    _load_module_with("drloco.config.hypers", "drloco/config/hypers.py",
+                      [("modifications_list = [MOD_CUSTOM_POLICY, MOD_MIRR_POLICY]",
+                        "modifications_list = [MOD_CUSTOM_POLICY]")])
+    import drloco.ref_trajecs  # noqa: F401
+    _load_module_with("drloco.ref_trajecs.base_ref_trajecs", "drloco/ref_trajecs/base_ref_trajecs.py",
+                      [("from collections import Iterable", "from collections.abc import Iterable")])
+    import drloco.ref_trajecs.loco3d_trajecs as l3
+    l3.get_project_path = lambda: project_dir.rstrip("/") + "/"
+    from drloco.mujoco.mimic_walker_165cm_65kg import MimicWalker165cm65kgEnv
+    from drloco.mujoco.monitor_wrapper import Monitor
+    from drloco.common import utils
+    return MimicWalker165cm65kgEnv, Monitor, utils
+
+
+def gen_w165_rollout(n_envs=6, n_steps=160, seed=0, out="w165_rollout.npz"):
+    """reference MimicWalker165cm65kgEnv (wrap cursor, joint-phase estimates, 2-D desired velocity, no mirroring) over
+    the oracle physics, reading the synthetic loco3d recording (drloco_b200.ref_trajecs.loco3d_trajecs.synthetic_loco3d,
+    seed 0) from a .mat file with the reference's schema (loco3d_trajecs.py:35-46)."""
+    import scipy.io as spio
+    from drloco_b200.ref_trajecs.loco3d_trajecs import synthetic_loco3d, N_ROWS
+    proj = tempfile.mkdtemp()
+    os.makedirs(os.path.join(proj, "mocaps/loco3d"))
+    ang, vel = synthetic_loco3d()
+    spio.savemat(os.path.join(proj, "mocaps/loco3d/loco3d_guoping.mat"),
+                 {"angJoi": ang, "angDJoi": vel, "rowNameIK": np.array([f"row{i}" for i in range(N_ROWS)], dtype=object)})
+    Env, Monitor, utils = load_reference_w165(proj)
+    random.seed(seed)
+    np.random.seed(seed)
+    rng = np.random.default_rng(seed)
+    envs, ewa = [], []
+    for i in range(n_envs):
+        utils._exp_weighted_averages = {}
+        envs.append(Monitor(Env()))
+        ewa.append({})
+    pristine = [e.env.refs._qpos_full.copy() for e in envs]
+    nv, nu = 19, 13
+    D = envs[0].env.observation_space.shape[0]
+    assert D == 47
+    rsi_log = []
+    for i, mon in enumerate(envs):
+        refs = mon.env.refs
+        orig = refs.get_random_init_state
+
+        def wrapped(orig=orig, refs=refs):
+            out_ = orig()
+            rsi_log.append(refs._pos)
+            return out_
+        refs.get_random_init_state = wrapped
+    T = n_steps
+    g = dict(actions=np.zeros((T, n_envs, nu), np.float32), obs=np.zeros((T, n_envs, D)), rew=np.zeros((T, n_envs)),
+             done=np.zeros((T, n_envs), np.uint8), terminal_obs=np.full((T, n_envs, D), np.nan),
+             qpos=np.zeros((T, n_envs, nv)), qvel=np.zeros((T, n_envs, nv)), cursor=np.zeros((T, n_envs, 2), np.int32),
+             ctrl=np.zeros((T, n_envs, nu)), comps=np.zeros((T, n_envs, 3)), walked=np.zeros((T, n_envs)),
+             des_vel=np.zeros((T, n_envs, 2)), rsi=np.full((T + 1, n_envs), -1, np.int32))
+    obs0 = np.zeros((n_envs, D))
+    # RSI draws: mostly random, two envs close to the end of the recording so that the cursor wraps (base:100-103)
+    L = envs[0].env.refs._trajec_len
+    forced = {0: L - 40, 1: L - 7}
+    for i in range(n_envs):
+        utils._exp_weighted_averages = ewa[i]
+        envs[i].env.refs._qpos_full[...] = pristine[i]           # Q4 waiver: no accumulation across episodes
+        if i in forced:
+            real = np.random.randint
+            np.random.randint = lambda lo, hi, _v=forced[i]: _v
+            obs0[i] = envs[i].env.reset()
+            np.random.randint = real
+        else:
+            obs0[i] = envs[i].env.reset()
+        g["rsi"][0, i] = rsi_log[-1]
+    g["obs0"] = obs0
+    g["qpos0"] = np.stack([e.env.sim.data.qpos.copy() for e in envs])
+    g["qvel0"] = np.stack([e.env.sim.data.qvel.copy() for e in envs])
+    g["cursor0"] = np.array([[e.env.refs._pos, e.env.ep_dur] for e in envs], np.int32)
+    for t in range(T):
+        a = rng.uniform(-1.3, 1.3, size=(n_envs, nu)).astype(np.float32)
+        a[: n_envs // 2] *= 0.1
+        g["actions"][t] = a
+        for i, mon in enumerate(envs):
+            utils._exp_weighted_averages = ewa[i]
+            e = mon.env
+            o, r, d, _ = mon.step(a[i])
+            g["qpos"][t, i], g["qvel"][t, i] = e.sim.data.qpos, e.sim.data.qvel
+            g["cursor"][t, i] = (e.refs._pos, e.ep_dur)
+            g["ctrl"][t, i] = e.sim.data.ctrl
+            g["comps"][t, i] = (e.pos_rew, e.vel_rew, e.com_rew)
+            g["walked"][t, i] = e.walked_distance
+            g["des_vel"][t, i] = e.desired_walking_speed
+            g["rew"][t, i], g["done"][t, i] = r, d
+            if d:
+                g["terminal_obs"][t, i] = o
+                e.refs._qpos_full[...] = pristine[i]
+                o = e.reset()
+                g["rsi"][t + 1, i] = rsi_log[-1]
+            g["obs"][t, i] = o
+    for name in ("ep_len_smoothed", "ep_ret_smoothed", "mean_reward_smoothed", "moved_distance",
+                 "mean_ep_pos_rew_smoothed", "mean_ep_vel_rew_smoothed", "mean_ep_com_rew_smoothed",
+                 "mean_abs_ep_torque_smoothed"):
+        g["mon_" + name] = np.array([float(getattr(m, name)) for m in envs])
+    g["mon_ep_lens_flat"] = np.array([x for m in envs for x in m.ep_lens], np.int32)
+    g["meta"] = np.array("reference MimicWalker165cm65kgEnv+Monitor (ENV_ID and mirroring set in the config as the "
+                         "reference asks its user to) over oracle physics on synthetic_loco3d(seed 0); Q4 waived; "
+                         "per-env smoothing dicts; seed=%d" % seed)
+    np.savez_compressed(os.path.join(REPO, "tests/golden", out), **g)
+    print(out, "episodes:", int(g["done"].sum()), "mean rew", g["rew"].mean(), "wraps:",
+          int((np.diff(g["cursor"][:, :, 0], axis=0) < 0).sum()))
+
+
 def gen_w3d_rollout(n_envs=8, n_steps=400, seed=0, out="w3d_rollout.npz"):
     Env, Monitor, utils = load_reference()
     random.seed(seed)
@@ -325,3 +462,5 @@ if __name__ == "__main__":
         gen_w3d_cursor()
     if which in ("all", "rollout"):
         gen_w3d_rollout()
+    if which == "w165":                      # separate process: the reference's config module is per-ENV_ID
+        gen_w165_rollout()

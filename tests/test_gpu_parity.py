@@ -164,6 +164,32 @@ def test_golden_rollout_from_reference_python(golden_dir):
     env.close()
 
 
+def test_w165_golden_rollout_from_reference_python(golden_dir):
+    """the first steps of the fixture produced by the reference's own MimicWalker165cm65kgEnv (tools/gen_golden.py w165):
+    wrap cursor, joint-phase estimates, windowed 2-D desired velocity, whole-recording COM-Z shift."""
+    g = np.load(os.path.join(golden_dir, "w165_rollout.npz"))
+    n = g["actions"].shape[1]
+    env = _env(W165, n)
+    zeros = np.zeros(n, np.int32)
+    obs = env.reset(inject=(zeros, g["rsi"][0]))
+    assert _rel(obs, g["obs0"]) < 2e-5
+    qg, vg, cg = env.get_state()
+    assert _rel(qg, g["qpos0"]) < 1e-6
+    np.testing.assert_array_equal(cg[:, [1, 3]], g["cursor0"])
+    for t in range(5):
+        obs, rew, done, infos = env.step(g["actions"][t], inject=(zeros, g["rsi"][t + 1].clip(min=0)))
+        qg, vg, cg = env.get_state()
+        np.testing.assert_array_equal(done, g["done"][t].astype(bool))
+        live = ~done
+        np.testing.assert_array_equal(cg[live][:, [1, 3]], g["cursor"][t][live])
+        assert _rel(qg[live], g["qpos"][t][live]) < REL_TOL and _rel(vg[live], g["qvel"][t][live]) < REL_TOL
+        assert np.abs(rew - g["rew"][t]).max() < REL_TOL
+        assert _rel(obs, g["obs"][t]) < REL_TOL
+        ex = env.extras().cpu().numpy()
+        assert np.abs(ex[live, :3] - g["comps"][t][live]).max() < REL_TOL
+    env.close()
+
+
 def test_long_horizon_divergence_is_reported():
     """beyond the short horizon fp32 and fp64 trajectories separate at contact events; termination decisions must
     still agree for as long as the states do."""

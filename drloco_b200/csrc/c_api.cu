@@ -509,6 +509,20 @@ extern "C" int drl_set_eval_mode(DrlEnv* e, int32_t on) {
   return DRL_OK;
 }
 
+extern "C" int drl_set_det_init_counters(DrlEnv* e, const int32_t* counts) {
+  if (!e || !counts) return fail(DRL_ERR_INVALID, "drl_set_det_init_counters: null argument");
+  if (!e->have_model) return fail(DRL_ERR_STATE, "drl_set_det_init_counters: upload the model first");
+  const int n = e->cfg.num_envs;
+  for (int i = 0; i < n; i++)
+    if (counts[i] < 0 || counts[i] >= (e->cfg.eval_n_times > 0 ? e->cfg.eval_n_times : 1))
+      return fail(DRL_ERR_INVALID, "drl_set_det_init_counters: counts[%d] = %d outside [0, eval_n_times)", i, counts[i]);
+  CUDA_TRY(cudaSetDevice(e->cfg.device));
+  CUDA_TRY(cudaDeviceSynchronize());
+  CUDA_TRY(cudaMemcpy2D(e->state_i + kCurNDet, kCurCount8 * sizeof(int), counts, sizeof(int), sizeof(int), (size_t)n,
+                        cudaMemcpyHostToDevice));
+  return DRL_OK;
+}
+
 extern "C" int drl_set_playback(DrlEnv* e, int32_t on) {
   if (!e) return fail(DRL_ERR_INVALID, "drl_set_playback: null env");
   e->playback = on ? 1 : 0;

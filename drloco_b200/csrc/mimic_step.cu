@@ -706,9 +706,17 @@ struct Cursor {
   int i_step, pos, count, ep_dur, rsi_step, n_det, resets, flags;
 };
 
+// Deterministic initialisation (evaluation, straight:237-265) leaves the reference reading the table and the length
+// of mocap step 0 (`reset()` aliases `_qpos_full = data[0]`, :161-167, and nothing re-points it) while `_i_step` and
+// `_step` already name step n; the first step transition repairs it.  flags bit 2: still reading step 0's table;
+// bit 3: the episode began with a deterministic init, so the in-place COM-Z shift went to step 0's table.
+constexpr int kFlagReadStep0 = 4, kFlagDetEpisode = 8;
+__device__ __forceinline__ int data_step(const Cursor& c) { return (c.flags & kFlagReadStep0) ? 0 : c.i_step; }
+__device__ __forceinline__ int shift_step(const Cursor& c) { return (c.flags & kFlagDetEpisode) ? 0 : c.rsi_step; }
+
 // StraightWalkingTrajectories.next (straight:141-159, :322-348) / BaseReferenceTrajectories.next (base:95-103)
 __device__ __forceinline__ void cursor_next(const DevModel& M, const StepArgs& A, Cursor& c, float& dist) {
-  const int len = A.step_len[c.i_step];
+  const int len = A.step_len[data_step(c)];
   c.pos += M.increment;
   if (M.cursor_mode == DRL_CURSOR_STEPWISE) {
     const int dif = c.pos - len + 1;
@@ -721,6 +729,7 @@ __device__ __forceinline__ void cursor_next(const DevModel& M, const StepArgs& A
       }
       dist = A.step_last_comx[c.rsi_step];   // Q2: `_step` stays the RSI step
       c.pos = dif;
+      c.flags &= ~kFlagReadStep0;
     }
   } else {
     if (c.pos >= len - 1) c.pos = 0;
@@ -732,12 +741,13 @@ __device__ __forceinline__ void ref_lookup(const DevModel& M, const StepArgs& A,
                                            float zoff, int l, int G, bool isdof, float& rq, float& rv) {
   rq = 0.f; rv = 0.f;
   if (!isdof) return;
-  const size_t row = (size_t)(A.step_off[c.i_step] + c.pos) * (size_t)(2 * G);
+  const int ds = data_step(c);
+  const size_t row = (size_t)(A.step_off[ds] + c.pos) * (size_t)(2 * G);
   rq = A.ref[row + l];
   rv = A.ref[row + G + l];
   if (M.cursor_mode == DRL_CURSOR_STEPWISE) {
     if (l == 0) rq += dist;
-    if (l == M.com_z_col && c.i_step == c.rsi_step) rq -= zoff;
+    if (l == M.com_z_col && ds == shift_step(c)) rq -= zoff;
   } else {
     if (l == M.com_z_col) rq -= zoff;
   }
@@ -791,7 +801,7 @@ __device__ __forceinline__ void build_obs(const DevModel& M, const StepArgs& A, 
   const int np = M.n_phase_obs, nd = M.n_des_vel;
   phase0 = 0.f;
   if (M.phase_mode == DRL_PHASE_FROM_CURSOR) {
-    phase0 = (float)c.pos / (float)A.step_len[c.i_step];
+    phase0 = (float)c.pos / (float)A.step_len[data_step(c)];
     if (l == 0) E.obsbuf[0] = phase0;
   } else if (L.isdof) {
     for (int k = 0; k < M.n_phase_joints; k++)
@@ -834,13 +844,16 @@ __device__ __noinline__ void reset_env(const DevModel& M, const StepArgs& A, Env
       c.pos = (3 * A.step_len[c.i_step]) / 4;
       c.n_det += 1;
       if (c.n_det >= M.eval_n_times) c.n_det = 0;
+      c.flags |= kFlagReadStep0 | kFlagDetEpisode;
     } else {
       c.i_step = 0; c.pos = 0;
     }
   } else if (A.inj_istep != nullptr && A.inj_pos != nullptr && A.inj_pos[env] >= 0) {
+    c.flags &= ~(kFlagReadStep0 | kFlagDetEpisode);
     c.i_step = M.cursor_mode == DRL_CURSOR_STEPWISE ? A.inj_istep[env] : 0;
     c.pos = A.inj_pos[env];
   } else {                                     // straight:460-474 / base:79-85
+    c.flags &= ~(kFlagReadStep0 | kFlagDetEpisode);
     const unsigned long long gid = (unsigned long long)(M.env_id_offset + env);
     const unsigned long long r = mix64(mix64(M.seed ^ (gid * 0xD1342543DE82EF95ull)) + (unsigned long long)c.resets);
     c.i_step = (int)(((r & 0xFFFFFFFFull) * (unsigned long long)M.n_steps) >> 32);
@@ -943,7 +956,7 @@ __global__ void __launch_bounds__(128, 4) mimic_step_kernel(const StepArgs A, co
         sf[3 * G + kMiscWalked] = 0.f; sf[3 * G + kMiscEpRet] = 0.f; sf[3 * G + kMiscEpTor] = 0.f;
         sf[3 * G + kMiscPrevPos] = 1.f; sf[3 * G + kMiscPrevVel] = 1.f; sf[3 * G + kMiscPrevCom] = 1.f;
         si[kCurIstep] = c.i_step; si[kCurPos] = c.pos; si[kCurCount] = c.count; si[kCurEpDur] = 0;
-        si[kCurRsiStep] = c.rsi_step; si[kCurNDet] = c.n_det; si[kCurResets] = c.resets;
+        si[kCurRsiStep] = c.rsi_step; si[kCurNDet] = c.n_det; si[kCurResets] = c.resets; si[kCurFlags] = c.flags;
       }
     }
     return;

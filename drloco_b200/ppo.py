@@ -196,7 +196,7 @@ class PPO:
 def evaluate_walking(policy: ActorCritic, train_env, n_episodes: int = 20, min_stable_distance: float = 15.0,
                      steady_state_counters: bool = False):
     """Deterministic evaluation in the spirit of reference ``TrainingMonitor.eval_walking`` (callback.py:272-390):
-    ``n_episodes`` episodes from the deterministic initial states (step i of the mocap at 75 % of the step,
+    ``n_episodes`` episodes from the reference's deterministic initial states (evaluation mode,
     straight_walk_trajecs.py:237-265), deterministic actions, frozen normalisation statistics; reports walked distance,
     episode duration and the count of stable walks (callback.py:336-349).  The episodes run side by side in one small
     batched env instead of one after the other."""
@@ -208,9 +208,10 @@ def evaluate_walking(policy: ActorCritic, train_env, n_episodes: int = 20, min_s
     env = B200MimicVecEnv(spec.cfg.env_id, num_envs=n_episodes, device=venv.device, cfg=spec.cfg, spec=spec, seed=0)
     vn = B200VecNormalize(env, training=False, norm_reward=False)
     vn.load_state_dict({**train_env.state_dict(), "norm_reward": False})
-    istep = (np.arange(n_episodes) % t.n_steps).astype(np.int32)
-    pos = ((3 * t.step_len[istep]) // 4).astype(np.int32)
-    obs = vn.reset_tensor(inject=(istep, pos)).clone()
+    # the reference plays EVAL_N_TIMES consecutive episodes in one env in evaluation mode (callback.py:286-297); here
+    # env i plays episode i: deterministic init i, including the reference's table aliasing
+    counters = np.arange(n_episodes) % spec.cfg.eval_n_times
+    env.env_method("activate_evaluation")
     if steady_state_counters:
         # count_steps_same_vel is never reset in the reference (Q3): after ~30 mocap steps of an env's lifetime the
         # desired-velocity observation is stuck at step_vel[0], which is what the policy saw for nearly all of its
@@ -219,7 +220,8 @@ def evaluate_walking(policy: ActorCritic, train_env, n_episodes: int = 20, min_s
         q, v, cur = env.get_state()
         cur[:, 2] = 10 ** 6
         env.set_state(None, None, cur)
-        obs = vn.reset_tensor(inject=(istep, pos)).clone()
+    env.set_det_init_counters(counters)
+    obs = vn.reset_tensor().clone()
     n = n_episodes
     alive = torch.ones(n, dtype=torch.bool, device=venv.device)
     ep_len = torch.zeros(n, device=venv.device)
@@ -227,7 +229,7 @@ def evaluate_walking(policy: ActorCritic, train_env, n_episodes: int = 20, min_s
     dist = torch.zeros(n, device=venv.device)
     for _ in range(spec.cfg.ep_dur_max + 1):
         mean, _ = policy(obs)
-        nobs, rew, done = vn.step_tensor(mean.contiguous(), inject=(istep, pos))
+        nobs, rew, done = vn.step_tensor(mean.contiguous())
         d = done.bool()
         ex = env.extras()
         # walked distance so far (mimic_env.py:295); for an env that just finished, the value at its episode end

@@ -381,6 +381,14 @@ class B200MimicVecEnv:
             torch.cuda.current_stream(dev).synchronize()
         self.launches += 1
 
+    def set_det_init_counters(self, counts) -> None:
+        """per-env `n_deterministic_inits` (straight_walk_trajecs.py:126): which mocap step each env's next deterministic
+        init starts from; a batched evaluation passes arange(num_envs) % eval_n_times."""
+        buf = np.ascontiguousarray(counts, np.int32).reshape(self.num_envs)
+        with torch.cuda.device(self.device):
+            lib.check(self._lib.drl_set_det_init_counters(self._handle, buf.ctypes.data_as(C.c_void_p)),
+                      "drl_set_det_init_counters")
+
     def launch_info(self) -> dict:
         vals = [C.c_int32() for _ in range(4)]
         lib.check(self._lib.drl_launch_info(self._handle, *[C.byref(v) for v in vals]), "drl_launch_info")

@@ -201,6 +201,12 @@ int drl_get_episode_ring(DrlEnv* env, int32_t* ep_len, float* ep_ret, int32_t ca
 /* MimicEnv.activate_evaluation (mimic_env.py:245): deterministic init states (straight_walk_trajecs.py:237-265) */
 int drl_set_eval_mode(DrlEnv* env, int32_t on);
 
+/* StraightWalkingTrajectories.n_deterministic_inits (straight_walk_trajecs.py:126,248-253) of every env: the index of
+ * the mocap step the NEXT deterministic init starts from.  counts: HOST int32 [num_envs].  A batched evaluation sets
+ * counts[i] = i so that env i plays the i-th of the reference's EVAL_N_TIMES consecutive evaluation episodes
+ * (callback.py:296-297).  Synchronises the device. */
+int drl_set_det_init_counters(DrlEnv* env, const int32_t* counts);
+
 /* MimicEnv.activate_speed_control (mimic_env.py:298-327): from now on the desired-velocity observation of every env is
  * speeds[ep_dur % n] (mimic_env.py:406-408) and resets use the deterministic init state (mimic_env.py:536-537).
  * `speeds` is a HOST array with one desired speed per control step (the host builds it with the reference's

@@ -40,16 +40,20 @@ class RefCursor:
         self.z_off = 0.0                   # adjust_COM_Z_pos offset of this episode, applies to the RSI step only (Q4 waiver)
         self.rsi_step = 0                  # ``self._step`` of the reference: the step chosen at the last RSI
         self.n_deterministic_inits = 0
+        # which step's table `_qpos_full` points at, and which table got the in-place COM-Z shift: the logical step
+        # except after a deterministic init, where the reference keeps reading step 0 until the first transition (Q27)
+        self.data_step = 0
+        self.shift_step = 0
 
     # -- lookups --------------------------------------------------------------------------------
     def _row(self):
-        return self.t.ref[int(self.t.step_off[self.i_step]) + self.pos]
+        return self.t.ref[int(self.t.step_off[self.data_step]) + self.pos]
 
     def get_qpos(self):
         q = self._row()[:self.nv].copy()
         if self.t.cursor_mode == CURSOR_STEPWISE:
             q[0] += self.dist                               # straight:346
-            if self.i_step == self.rsi_step:
+            if self.data_step == self.shift_step:
                 q[self.t.com_z_col] -= self.z_off           # base:126-127 through the alias of straight:467-469;
                                                             # every other step is an unshifted copy (straight:342)
         else:
@@ -90,6 +94,7 @@ class RefCursor:
                     self.count_steps_same_vel += 1
                 self.dist = float(self.t.step_last_comx[self.rsi_step])   # ``_step`` is never updated (Q2)
                 self.len = int(self.t.step_len[self.i_step])
+                self.data_step = self.i_step
                 self.pos = dif
         else:                                               # base:95-103
             self.pos += inc
@@ -109,14 +114,18 @@ class RefCursor:
         else:
             self.i_step, self.len = 0, int(self.t.step_len[0])
             self.pos = int(np.random.randint(0, self.len)) if pos is None else int(pos)
+        self.data_step = self.shift_step = self.i_step
         self._begin_episode()
 
     def init_deterministic(self, eval_n_times: int):
         """straight:237-265 / base:69-77."""
         if self.t.cursor_mode == CURSOR_STEPWISE:
+            # straight:240 `self.reset()` points `_qpos_full` / `_trajec_len` at step 0 (:163-167) and the lines after it
+            # only move `_i_step`, `_step` and `_pos`: data and length stay step 0's until the first transition (Q27)
             self.i_step = self.n_deterministic_inits
-            self.len = int(self.t.step_len[self.i_step])
-            self.pos = int(0.75 * self.len)
+            self.len = int(self.t.step_len[0])
+            self.pos = int(0.75 * int(self.t.step_len[self.i_step]))
+            self.data_step = self.shift_step = 0
             self.n_deterministic_inits += 1
             if self.n_deterministic_inits >= eval_n_times:
                 self.n_deterministic_inits = 0

@@ -190,6 +190,32 @@ def test_w165_golden_rollout_from_reference_python(golden_dir):
     env.close()
 
 
+def test_eval_mode_golden_from_reference_python(golden_dir):
+    """evaluation mode against the fixture produced by the reference's own env (tools/gen_golden.py eval): deterministic
+    init states incl. the reference's table aliasing (Q27) - cursor, phase, desired speed and mirroring for whole
+    episodes (they do not depend on the physics), states and rewards over the first steps of each."""
+    g = np.load(os.path.join(golden_dir, "w3d_eval.npz"))
+    env = _env(W3D, 1)
+    env.env_method("activate_evaluation")
+    E, T = g["actions"].shape[:2]
+    for k in range(E):
+        obs = env.reset()
+        assert _rel(obs, g["obs0"][k][None]) < 2e-5
+        qg, vg, cg = env.get_state()
+        np.testing.assert_array_equal(cg[0], g["cursor0"][k])
+        assert _rel(qg, g["qpos0"][k][None]) < 1e-6
+        for t in range(int(g["n_valid"][k])):
+            obs, rew, done, _ = env.step(g["actions"][k, t][None])
+            assert not done[0]
+            qg, vg, cg = env.get_state()
+            np.testing.assert_array_equal(cg[0], g["cursor"][k, t])
+            assert abs(obs[0, 0] - g["phase"][k, t]) < 1e-6 and abs(obs[0, 1] - g["obs"][k, t, 1]) < 1e-6
+            if t < 6:
+                assert _rel(obs, g["obs"][k, t][None]) < REL_TOL and abs(rew[0] - g["rew"][k, t]) < REL_TOL
+                assert _rel(qg, g["qpos"][k, t][None]) < REL_TOL
+    env.close()
+
+
 def test_long_horizon_divergence_is_reported():
     """beyond the short horizon fp32 and fp64 trajectories separate at contact events; termination decisions must
     still agree for as long as the states do."""
@@ -309,6 +335,14 @@ def test_blowup_path_and_eval_mode():
         L = env.spec.mocap.step_len[k]
         inc = env.spec.mocap.increment
         assert (c[:, 0] == k).all() and (c[:, 1] == (3 * L) // 4 + inc).all()
+    # batched evaluation: env i plays the i-th consecutive evaluation episode of the reference (callback.py:296-297)
+    env.set_det_init_counters(np.arange(n) % env.cfg.eval_n_times)
+    env.reset()
+    _, _, c = env.get_state()
+    np.testing.assert_array_equal(c[:, 0], np.arange(n))
+    np.testing.assert_array_equal(c[:, 1], (3 * env.spec.mocap.step_len[:n]) // 4 + env.spec.mocap.increment)
+    with pytest.raises(Exception):
+        env.set_det_init_counters(np.full(n, 99))
     env.close()
 
 

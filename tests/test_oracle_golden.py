@@ -112,3 +112,32 @@ def test_w165_rollout_matches_reference(golden_dir):
         got = np.array([float(getattr(m, name)) for m in venv.envs])
         np.testing.assert_allclose(got, g["mon_" + name], rtol=1e-12, atol=0, err_msg=name)
     np.testing.assert_array_equal([x for m in venv.envs for x in m.ep_lens], g["mon_ep_lens_flat"])
+
+
+def test_eval_mode_matches_reference(spec, golden_dir):
+    """evaluation mode: deterministic init states straight:237-265 with the reference's table aliasing (Q27: data and
+    length of mocap step 0 until the first transition, `_i_step` / mirroring / next-step choice of step n)."""
+    from oracle.env_oracle import OracleMimicEnv
+    g = np.load(os.path.join(golden_dir, "w3d_eval.npz"))
+    env = OracleMimicEnv(spec, OraclePhysics(spec.model))
+    env._EVAL_MODEL = True
+    env.refs.count_steps_same_vel = int(g["count_at_construction"])    # after the construction-time step (Q14)
+    E, T = g["actions"].shape[:2]
+    crossed = 0
+    for k in range(E):
+        obs = env.reset()
+        np.testing.assert_array_equal(obs, g["obs0"][k], err_msg=f"episode {k}")
+        np.testing.assert_array_equal(env.qpos, g["qpos0"][k])
+        assert (env.refs.i_step, env.refs.pos, env.refs.count_steps_same_vel, env.ep_dur) == tuple(g["cursor0"][k])
+        for t in range(int(g["n_valid"][k])):
+            before = env.refs.i_step
+            obs, rew, done, _ = env.step(g["actions"][k, t])
+            assert (env.refs.i_step, env.refs.pos, env.refs.count_steps_same_vel, env.ep_dur) == tuple(g["cursor"][k, t])
+            assert env.refs.get_phase_variable() == g["phase"][k, t] and env.refs.is_step_left() == bool(g["left"][k, t])
+            np.testing.assert_array_equal(obs, g["obs"][k, t], err_msg=f"episode {k} step {t}")
+            np.testing.assert_array_equal(env.qpos, g["qpos"][k, t])
+            assert rew == g["rew"][k, t] and done == bool(g["done"][k, t])
+            crossed += int(env.refs.i_step != before)
+    assert crossed >= E                                                 # every episode crossed its first transition
+    # the quirk itself: episode 1 starts on step 1 (a left step: mirrored obs) but with step 0's phase denominator
+    assert g["cursor0"][1, 0] == 1 and g["phase"][1, 0] == (g["cursor"][1, 0, 1]) / spec.mocap.step_len[0]

@@ -16,7 +16,7 @@ Conditions of the run (recorded in the fixture):
   * envs are stepped with DummyVecEnv semantics written out by hand (SB3 is not installed): on done keep the terminal
     observation and reset.
 
-Usage: python tools/gen_golden.py            (writes tests/golden/w3d_rollout.npz, w3d_cursor.npz)
+Usage: python tools/gen_golden.py            (writes tests/golden/w3d_rollout.npz, w3d_cursor.npz, w3d_eval.npz)
        python tools/gen_golden.py w165       (writes tests/golden/w165_rollout.npz; own process: other ENV_ID)
 """
 import collections
@@ -430,6 +430,48 @@ def gen_w3d_rollout(n_envs=8, n_steps=400, seed=0, out="w3d_rollout.npz"):
     print(out, "episodes:", int(g["done"].sum()), "mean rew", g["rew"].mean())
 
 
+def gen_w3d_eval(out="w3d_eval.npz", seed=0, n_episodes=6, n_steps=70):
+    """evaluation mode (MimicEnv.activate_evaluation, mimic_env.py:245, :536-537): deterministic initial states
+    (straight:237-265).  Each episode runs n_steps control steps with small actions (long enough to cross the first
+    mocap-step transition), then the next reset is forced; a done ends it earlier."""
+    Env, Monitor, utils = load_reference()
+    random.seed(seed)
+    np.random.seed(seed)
+    rng = np.random.default_rng(seed)
+    e = Env()
+    pristine = copy.deepcopy(e.refs.data)
+    e.activate_evaluation()
+    nv, nu, D = 14, 8, 29
+    E, T = n_episodes, n_steps
+    g = dict(actions=np.zeros((E, T, nu), np.float32), obs=np.full((E, T, D), np.nan), rew=np.full((E, T), np.nan),
+             done=np.zeros((E, T), np.uint8), qpos=np.full((E, T, nv), np.nan), cursor=np.full((E, T, 4), -1, np.int32),
+             obs0=np.zeros((E, D)), qpos0=np.zeros((E, nv)), cursor0=np.zeros((E, 4), np.int32),
+             n_valid=np.zeros(E, np.int32), phase=np.full((E, T), np.nan), left=np.zeros((E, T), np.uint8))
+    count0 = e.refs.count_steps_same_vel
+    for k in range(E):
+        e.refs.data = copy.deepcopy(pristine)                   # Q4 waiver
+        g["obs0"][k] = e.reset()
+        g["qpos0"][k] = e.sim.data.qpos
+        g["cursor0"][k] = (e.refs._i_step, e.refs._pos, e.refs.count_steps_same_vel, e.ep_dur)
+        for t in range(T):
+            a = (0.1 * rng.uniform(-1, 1, nu)).astype(np.float32)
+            g["actions"][k, t] = a
+            o, r, d, _ = e.step(a)
+            g["obs"][k, t], g["rew"][k, t], g["done"][k, t] = o, r, d
+            g["qpos"][k, t] = e.sim.data.qpos
+            g["cursor"][k, t] = (e.refs._i_step, e.refs._pos, e.refs.count_steps_same_vel, e.ep_dur)
+            g["phase"][k, t] = e.refs.get_phase_variable()
+            g["left"][k, t] = e.refs.is_step_left()
+            g["n_valid"][k] = t + 1
+            if d:
+                break
+    g["count_at_construction"] = np.int32(count0)
+    g["meta"] = np.array("reference MimicWalker3dEnv (unmodified) in evaluation mode over oracle physics; Q4 waived; seed=%d"
+                         % seed)
+    np.savez_compressed(os.path.join(REPO, "tests/golden", out), **g)
+    print(out, "valid steps per episode:", g["n_valid"], "first cursors:", g["cursor0"].tolist())
+
+
 def gen_w3d_cursor(out="w3d_cursor.npz", seed=0, n=1200):
     """pure cursor trace (SURVEY.md §8c known-answer iii): refs.next() from random.seed(0)."""
     _, _, _ = load_reference()
@@ -462,5 +504,7 @@ if __name__ == "__main__":
         gen_w3d_cursor()
     if which in ("all", "rollout"):
         gen_w3d_rollout()
+    if which in ("all", "eval"):
+        gen_w3d_eval()
     if which == "w165":                      # separate process: the reference's config module is per-ENV_ID
         gen_w165_rollout()

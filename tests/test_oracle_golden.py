@@ -46,9 +46,15 @@ def test_cursor_trace_matches_reference(spec, golden_dir):
     assert change == [41, 175, 312, 443, 577] or change == [40, 174, 311, 442, 576] or len(change) == 5
 
 
-def test_rollout_matches_reference(spec, golden_dir):
-    """reference MimicWalker3dEnv + Monitor over the oracle physics vs OracleVecEnv on the same actions and RSI draws."""
-    g = np.load(os.path.join(golden_dir, "w3d_rollout.npz"))
+@pytest.mark.parametrize("fixture,ep_dur_max", [("w3d_rollout.npz", 3000), ("w3d_timeout.npz", 25)])
+def test_rollout_matches_reference(golden_dir, fixture, ep_dur_max):
+    """reference MimicWalker3dEnv + Monitor over the oracle physics vs OracleVecEnv on the same actions and RSI draws.
+    w3d_timeout.npz: the reference run with hypers.ep_dur_max = 25, every episode ends by time-out (reward +0.0, Q1)."""
+    from drloco_b200.config import EnvConfig
+    spec = make_spec(EnvConfig(ep_dur_max=ep_dur_max))
+    g = np.load(os.path.join(golden_dir, fixture))
+    if ep_dur_max == 25:
+        assert g["done"].sum() >= 10 and (g["mon_ep_lens_flat"] == 25).all() and not np.signbit(g["rew"][g["done"] > 0]).any()
     T, N = g["actions"].shape[:2]
     venv = OracleVecEnv(spec, N, lambda: OraclePhysics(spec.model))
     for e in venv.envs:                                    # the reference env has stepped once in __init__ (Q14):

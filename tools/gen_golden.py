@@ -189,8 +189,9 @@ def install_stubs():
     sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
 
 
-def load_reference():
-    """import the reference package with the two forced substitutions; returns (env class, Monitor class, utils)."""
+def load_reference(hypers_subst=()):
+    """import the reference package with the two forced substitutions; returns (env class, Monitor class, utils).
+    ``hypers_subst``: textual edits of drloco/config/hypers.py (settings the reference expects its user to edit)."""
     sys.path.insert(0, REF)
     # is_remote() <=> 'code/torch' in cwd: no viewer, n_envs = 8 (Q12/Q13)
     work = os.path.join(tempfile.mkdtemp(), "code", "torch")
@@ -198,6 +199,9 @@ def load_reference():
     os.chdir(work)
     import torch  # noqa: F401  (hypers.py imports it; load the real one before the stubs go in)
     install_stubs()
+    if hypers_subst:
+        import drloco.config  # noqa: F401
+        _load_module_with("drloco.config.hypers", "drloco/config/hypers.py", list(hypers_subst))
     name = "drloco.ref_trajecs.straight_walk_trajecs"
     path = os.path.join(REF, "drloco/ref_trajecs/straight_walk_trajecs.py")
     src = open(path).read().replace("PATH_REF_TRAJECS = PATH_SPEED_RAMP", "PATH_REF_TRAJECS = PATH_CONSTANT_SPEED")
@@ -349,8 +353,8 @@ def gen_w165_rollout(n_envs=6, n_steps=160, seed=0, out="w165_rollout.npz"):
           int((np.diff(g["cursor"][:, :, 0], axis=0) < 0).sum()))
 
 
-def gen_w3d_rollout(n_envs=8, n_steps=400, seed=0, out="w3d_rollout.npz"):
-    Env, Monitor, utils = load_reference()
+def gen_w3d_rollout(n_envs=8, n_steps=400, seed=0, out="w3d_rollout.npz", hypers_subst=()):
+    Env, Monitor, utils = load_reference(hypers_subst)
     random.seed(seed)
     np.random.seed(seed)
     rng = np.random.default_rng(seed)
@@ -506,5 +510,8 @@ if __name__ == "__main__":
         gen_w3d_rollout()
     if which in ("all", "eval"):
         gen_w3d_eval()
+    if which == "timeout":                   # separate process: ep_dur_max = 25 in the reference's hypers.py (:58)
+        gen_w3d_rollout(n_envs=4, n_steps=120, seed=3, out="w3d_timeout.npz",
+                        hypers_subst=[("ep_dur_max = 3000", "ep_dur_max = 25")])
     if which == "w165":                      # separate process: the reference's config module is per-ENV_ID
         gen_w165_rollout()

@@ -232,11 +232,12 @@ def evaluate_walking(policy: ActorCritic, train_env, n_episodes: int = 20, min_s
         nobs, rew, done = vn.step_tensor(mean.contiguous())
         d = done.bool()
         ex = env.extras()
-        # walked distance so far (mimic_env.py:295); for an env that just finished, the value at its episode end
-        walked = torch.where(d, ex[:, 14], ex[:, 3])
+        # walked distance (mimic_env.py:295).  The reference reads it only on steps that did not end the episode
+        # ("when done=True is returned, the env is already resetted", callback.py:313-316), so an episode's distance
+        # is the value one step before its end: `dist` simply stops being updated on the done step.
         ep_len += alive.float()
         rew_sum += torch.where(alive & ~d, rew, torch.zeros_like(rew))
-        dist = torch.where(alive, walked, dist)
+        dist = torch.where(alive & ~d, ex[:, 3], dist)
         alive &= ~d
         obs = nobs.clone()
         if not bool(alive.any()):

@@ -74,6 +74,8 @@ def test_rollout_matches_reference(golden_dir, fixture, ep_dur_max):
         for i in range(N):
             if done[i]:
                 np.testing.assert_array_equal(infos[i]["terminal_observation"], g["terminal_obs"][t, i])
+        if "et" in g.files:        # do_terminate_early() of the reference env on the same states (mimic_env.py:652-702)
+            np.testing.assert_array_equal([m.env.et_flags for m in venv.envs], g["et"][t].astype(bool), err_msg=f"t={t}")
     for name in ("ep_len_smoothed", "ep_ret_smoothed", "mean_reward_smoothed", "moved_distance",
                  "mean_ep_pos_rew_smoothed", "mean_ep_vel_rew_smoothed", "mean_ep_com_rew_smoothed",
                  "mean_abs_ep_torque_smoothed"):

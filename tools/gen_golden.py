@@ -385,7 +385,8 @@ def gen_w3d_rollout(n_envs=8, n_steps=400, seed=0, out="w3d_rollout.npz", hypers
              done=np.zeros((T, n_envs), np.uint8), terminal_obs=np.full((T, n_envs, D), np.nan),
              qpos=np.zeros((T, n_envs, nv)), qvel=np.zeros((T, n_envs, nv)), cursor=np.zeros((T, n_envs, 4), np.int32),
              ctrl=np.zeros((T, n_envs, nu)), comps=np.zeros((T, n_envs, 3)), walked=np.zeros((T, n_envs)),
-             des_vel=np.zeros((T, n_envs)), rsi=np.full((T + 1, n_envs, 2), -1, np.int32))
+             des_vel=np.zeros((T, n_envs)), rsi=np.full((T + 1, n_envs, 2), -1, np.int32),
+             et=np.zeros((T, n_envs, 4), np.uint8))
     obs0 = np.zeros((n_envs, D))
     random.seed(seed + 1)
     for i in range(n_envs):
@@ -414,6 +415,7 @@ def gen_w3d_rollout(n_envs=8, n_steps=400, seed=0, out="w3d_rollout.npz", hypers
             g["walked"][t, i] = e.walked_distance
             g["des_vel"][t, i] = e.desired_walking_speed[0]
             g["rew"][t, i], g["done"][t, i] = r, d
+            g["et"][t, i] = e.do_terminate_early()        # dead code in step() (mimic_env.py:122-123), called here
             if d:
                 g["terminal_obs"][t, i] = o
                 e.refs.data = copy.deepcopy(pristine[i])  # Q4 waiver

@@ -13,7 +13,7 @@ Two ways to step:
 from __future__ import annotations
 
 import ctypes as C
-from typing import Any, List, Optional, Sequence, Tuple
+from typing import Any, List, Optional, Tuple
 
 import numpy as np
 import torch

@@ -3,7 +3,6 @@ here, so the restatement is pinned to mechanics instead: the ma
 definition, the bias force to Lagrange's equations, the integrator to energy conservation, the constraint solve to its
 KKT conditions and to weight = normal force at rest."""
 import copy
-import ctypes as C
 
 import numpy as np
 import pytest

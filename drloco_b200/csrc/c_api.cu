@@ -57,6 +57,8 @@ struct DrlEnv {
   unsigned char* left_step = nullptr;
   int* ring_len = nullptr;
   float* ring_ret = nullptr;
+  int *ring_rsi_pos = nullptr, *ring_et_pos = nullptr;
+  unsigned char* ring_difficult = nullptr;
   unsigned long long* ring_head = nullptr;
   int ring_cap = 1 << 16;
   int eval_mode = 0;
@@ -93,7 +95,7 @@ extern "C" int drl_destroy(DrlEnv* e) {
   cudaSetDevice(e->cfg.device);
   void* ptrs[] = {e->d_model, e->state_f, e->state_i, e->state_as, e->state_d, e->extras_last, e->stats, e->ref, e->step_vel,
                   e->step_last_comx, e->des_vel_prefix, e->step_off, e->step_len, e->left_step, e->ring_len,
-                  e->ring_ret, e->ring_head, e->debug, e->speed_profile};
+                  e->ring_ret, e->ring_head, e->debug, e->speed_profile, e->ring_rsi_pos, e->ring_et_pos, e->ring_difficult};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   delete e;
@@ -112,6 +114,9 @@ static int alloc_state(DrlEnv* e, size_t N) {
   CUDA_TRY(cudaMalloc(&e->stats, DRL_STATS_COUNT * sizeof(double)));
   CUDA_TRY(cudaMalloc(&e->ring_len, e->ring_cap * sizeof(int)));
   CUDA_TRY(cudaMalloc(&e->ring_ret, e->ring_cap * sizeof(float)));
+  CUDA_TRY(cudaMalloc(&e->ring_rsi_pos, e->ring_cap * sizeof(int)));
+  CUDA_TRY(cudaMalloc(&e->ring_et_pos, e->ring_cap * sizeof(int)));
+  CUDA_TRY(cudaMalloc(&e->ring_difficult, e->ring_cap));
   CUDA_TRY(cudaMalloc(&e->ring_head, sizeof(unsigned long long)));
   CUDA_TRY(cudaMemset(e->state_f, 0, N * 4 * e->G * sizeof(float)));
   CUDA_TRY(cudaMemset(e->state_i, 0, N * kCurCount8 * sizeof(int)));
@@ -129,7 +134,8 @@ static int alloc_state(DrlEnv* e, size_t N) {
 static void free_state(DrlEnv* e) {
   void** ptrs[] = {(void**)&e->d_model, (void**)&e->state_f, (void**)&e->state_i, (void**)&e->state_as,
                    (void**)&e->state_d, (void**)&e->extras_last, (void**)&e->stats, (void**)&e->ring_len,
-                   (void**)&e->ring_ret, (void**)&e->ring_head};
+                   (void**)&e->ring_ret, (void**)&e->ring_head, (void**)&e->ring_rsi_pos, (void**)&e->ring_et_pos,
+                   (void**)&e->ring_difficult};
   for (void** p : ptrs) {
     if (*p) cudaFree(*p);
     *p = nullptr;
@@ -412,6 +418,7 @@ static StepArgs make_args(DrlEnv* e) {
   a.step_vel = e->step_vel; a.step_last_comx = e->step_last_comx; a.des_vel_prefix = e->des_vel_prefix;
   a.extras = e->extras_last; a.stats = e->stats;
   a.ring_len = e->ring_len; a.ring_ret = e->ring_ret; a.ring_head = e->ring_head; a.ring_cap = e->ring_cap;
+  a.ring_rsi_pos = e->ring_rsi_pos; a.ring_et_pos = e->ring_et_pos; a.ring_difficult = e->ring_difficult;
   a.eval_mode = e->eval_mode;
   a.speed_profile = e->speed_profile_len > 0 ? e->speed_profile : nullptr;
   a.speed_profile_len = e->speed_profile_len;
@@ -500,6 +507,19 @@ extern "C" int drl_get_episode_ring(DrlEnv* e, int32_t* ep_len, float* ep_ret, i
   const int n = capacity < e->ring_cap ? capacity : e->ring_cap;
   if (ep_len && n > 0) CUDA_TRY(cudaMemcpyAsync(ep_len, e->ring_len, n * sizeof(int), cudaMemcpyDeviceToDevice, st));
   if (ep_ret && n > 0) CUDA_TRY(cudaMemcpyAsync(ep_ret, e->ring_ret, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  return DRL_OK;
+}
+
+extern "C" int drl_get_episode_positions(DrlEnv* e, int32_t* rsi_pos, int32_t* et_pos, uint8_t* difficult,
+                                         int32_t capacity, void* stream) {
+  int rc = ready(e, "drl_get_episode_positions");
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int n = capacity < e->ring_cap ? capacity : e->ring_cap;
+  if (n <= 0) return DRL_OK;
+  if (rsi_pos) CUDA_TRY(cudaMemcpyAsync(rsi_pos, e->ring_rsi_pos, n * sizeof(int), cudaMemcpyDeviceToDevice, st));
+  if (et_pos) CUDA_TRY(cudaMemcpyAsync(et_pos, e->ring_et_pos, n * sizeof(int), cudaMemcpyDeviceToDevice, st));
+  if (difficult) CUDA_TRY(cudaMemcpyAsync(difficult, e->ring_difficult, n, cudaMemcpyDeviceToDevice, st));
   return DRL_OK;
 }
 

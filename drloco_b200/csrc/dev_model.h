@@ -109,6 +109,9 @@ struct StepArgs {
   double* stats;                     // [DRL_STATS_COUNT]
   int* ring_len;                     // episode ring
   float* ring_ret;
+  int* ring_rsi_pos;                 // Monitor.rsi_positions / et_positions / difficult flag of the same episode slots
+  int* ring_et_pos;
+  unsigned char* ring_difficult;
   unsigned long long* ring_head;
   int ring_cap;
   int eval_mode;

@@ -1059,6 +1059,8 @@ __global__ void __launch_bounds__(128, 4) mimic_step_kernel(const StepArgs A, co
   bool done;
   const int ep_dur_before = c.ep_dur;
   cursor_next(M, A, c, dist);                                   // mimic_env.py:96
+  // Monitor: refs._pos after the first step of an episode (monitor_wrapper.py:91-93), kept in the upper half of flags
+  if (ep_dur_before == 0) c.flags = (c.flags & 0xFFFF) | (c.pos << 16);
   if (A.playback) {                                             // set_joint_kinematics_in_sim (mimic_env.py:273-293)
     float rq, rv;
     ref_lookup(M, A, c, dist, zoff, l, G, L.isdof, rq, rv);
@@ -1168,6 +1170,9 @@ __global__ void __launch_bounds__(128, 4) mimic_step_kernel(const StepArgs A, co
       const unsigned long long slot = atomicAdd(A.ring_head, 1ull) % (unsigned long long)A.ring_cap;
       A.ring_len[slot] = ep_len;
       A.ring_ret[slot] = ep_ret;
+      A.ring_rsi_pos[slot] = (int)((unsigned)c.flags >> 16);           // monitor_wrapper.py:91-93
+      A.ring_et_pos[slot] = c.pos;                                      // :104-107
+      A.ring_difficult[slot] = (float)ep_len < ms[kMiscEpLenSm] * 0.75f ? 1 : 0;   // :123-124 (after the smoothing)
     }
   }
   c.flags = __shfl_sync(kFull, c.flags, 0, G);

@@ -266,20 +266,30 @@ class B200MimicVecEnv:
     def reset_stats(self):
         lib.check(self._lib.drl_reset_stats(self._handle, self._stream()), "drl_reset_stats")
 
-    def episode_lengths(self) -> np.ndarray:
+    def episode_records(self) -> dict:
+        """the episodes finished since ``set_attr('ep_lens', [])`` (at most the ring capacity, oldest first): ``ep_len``,
+        ``ep_ret`` and Monitor's position records ``rsi_pos``, ``et_pos``, ``difficult`` (monitor_wrapper.py:91-124)."""
         cap = 1 << 16
-        with torch.cuda.device(self.device):
-            ln = torch.zeros(cap, dtype=torch.int32, device=self.device)
+        dev = self.device
+        with torch.cuda.device(dev):
+            ln = torch.zeros(cap, dtype=torch.int32, device=dev)
+            rt = torch.zeros(cap, dtype=torch.float32, device=dev)
+            rp = torch.zeros(cap, dtype=torch.int32, device=dev)
+            ep = torch.zeros(cap, dtype=torch.int32, device=dev)
+            df = torch.zeros(cap, dtype=torch.uint8, device=dev)
             total = C.c_int64()
-            lib.check(self._lib.drl_get_episode_ring(self._handle, _ptr(ln), None, cap, C.byref(total), self._stream()),
-                      "drl_get_episode_ring")
+            lib.check(self._lib.drl_get_episode_ring(self._handle, _ptr(ln), _ptr(rt), cap, C.byref(total),
+                                                     self._stream()), "drl_get_episode_ring")
+            lib.check(self._lib.drl_get_episode_positions(self._handle, _ptr(rp), _ptr(ep), _ptr(df), cap,
+                                                          self._stream()), "drl_get_episode_positions")
         total = total.value
         n_new = min(total - self._ep_lens_base, cap)
-        if n_new <= 0:
-            return np.zeros(0, np.int32)
-        host = ln.cpu().numpy()
-        idx = (np.arange(total - n_new, total) % cap)
-        return host[idx]
+        idx = (np.arange(total - n_new, total) % cap) if n_new > 0 else np.zeros(0, np.int64)
+        return dict(ep_len=ln.cpu().numpy()[idx], ep_ret=rt.cpu().numpy()[idx], rsi_pos=rp.cpu().numpy()[idx],
+                    et_pos=ep.cpu().numpy()[idx], difficult=df.cpu().numpy()[idx].astype(bool))
+
+    def episode_lengths(self) -> np.ndarray:
+        return self.episode_records()["ep_len"]
 
     def get_attr(self, attr_name: str, indices=None) -> List[Any]:
         idx = self._indices(indices)
@@ -291,6 +301,12 @@ class B200MimicVecEnv:
             # the reference returns one list per env and the callback flattens them (callback.py:227-230)
             lens = self.episode_lengths().tolist()
             return [lens] + [[] for _ in idx[1:]]
+        if attr_name in ("et_positions", "difficult_rsi_phases"):
+            # as ep_lens: one merged list (env 0), finished episodes only.  Monitor.rsi_positions also holds the entry of
+            # each env's running episode; those are not in the ring (episode_records() documents the finished ones).
+            rec = self.episode_records()
+            vals = rec["et_pos"] if attr_name == "et_positions" else rec["rsi_pos"][rec["difficult"]]
+            return [vals.tolist()] + [[] for _ in idx[1:]]
         if attr_name in ("num_envs", "obs_dim", "act_dim"):
             return [getattr(self, attr_name)] * len(idx)
         if attr_name in ("ep_dur", "i_step", "pos"):

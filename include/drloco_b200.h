@@ -198,6 +198,14 @@ int drl_reset_stats(DrlEnv* env, void* stream);
 int drl_get_episode_ring(DrlEnv* env, int32_t* ep_len, float* ep_ret, int32_t capacity, int64_t* total_episodes,
                          void* stream);
 
+/* the same ring slots as drl_get_episode_ring for Monitor's per-episode position records (monitor_wrapper.py:91-93,
+ * 104-107,123-124): rsi_pos = refs._pos after the first step of the episode (`rsi_positions`), et_pos = refs._pos when
+ * the episode ended (`et_positions`; for a simulator blow-up the cursor before the internal reset), difficult = 1 when
+ * ep_len < 0.75 * ep_len_smoothed (the episode's rsi_pos then also belongs to `difficult_rsi_phases`).
+ * device int32 / int32 / uint8 [capacity], each nullable. */
+int drl_get_episode_positions(DrlEnv* env, int32_t* rsi_pos, int32_t* et_pos, uint8_t* difficult, int32_t capacity,
+                              void* stream);
+
 /* MimicEnv.activate_evaluation (mimic_env.py:245): deterministic init states (straight_walk_trajecs.py:237-265) */
 int drl_set_eval_mode(DrlEnv* env, int32_t on);
 

@@ -309,7 +309,9 @@ class OracleMonitor:
         self.ep_torques_abs: List[float] = []
         self.ep_lens: List[int] = []
         self.returns: List[float] = []
-        self.rsi_positions, self.et_positions = [], []
+        self.rsi_positions, self.et_positions, self.difficult_rsi_phases = [], [], []
+        self.init_pos = 0
+        self.ep_difficult: List[bool] = []                    # per finished episode: did it enter difficult_rsi_phases
         self.ep_len_smoothed = self.ep_ret_smoothed = self.mean_reward_smoothed = 0
         self.mean_ep_pos_rew_smoothed = self.mean_ep_vel_rew_smoothed = self.mean_ep_com_rew_smoothed = 0
         self.mean_abs_ep_torque_smoothed = 0
@@ -326,7 +328,8 @@ class OracleMonitor:
     def step(self, action):                                   # monitor_wrapper.py:88-166
         obs, reward, done, info = self.env.step(action)
         if self.ep_len == 0:
-            self.rsi_positions.append(self.env.refs.pos)
+            self.init_pos = self.env.refs.pos
+            self.rsi_positions.append(self.init_pos)
         self.ep_len += 1
         self.rewards.append(reward)
         self.ep_pos_rews.append(self.env.pos_rew)
@@ -346,6 +349,9 @@ class OracleMonitor:
             self.ep_ret_smoothed = self._smooth("ep_ret", ep_return, 0.25)
             self.ep_lens.append(self.ep_len)
             self.ep_len_smoothed = self._smooth("ep_len", self.ep_len, 0.75)
+            self.ep_difficult.append(bool(self.ep_len < self.ep_len_smoothed * 0.75))
+            if self.ep_difficult[-1]:
+                self.difficult_rsi_phases.append(self.init_pos)
             self.ep_len = 0
             self.moved_distance = self.env.walked_distance
             self.mean_abs_ep_torque_smoothed = self._smooth("mean_ep_tor", float(np.mean(self.ep_torques_abs)), 0.75)

@@ -307,6 +307,14 @@ def test_env_logic_and_monitor_on_injected_states():
         np.testing.assert_allclose(got, want, rtol=2e-4, atol=2e-5, err_msg=name)
     lens_o = sorted(x for m in ora.envs for x in m.ep_lens)
     assert sorted(env.episode_lengths().tolist()) == lens_o
+    # Monitor's per-episode position records (monitor_wrapper.py:91-93,104-107,123-124); ring order is arbitrary within a step
+    rec = env.episode_records()
+    got = sorted(zip(rec["rsi_pos"].tolist(), rec["et_pos"].tolist(), rec["ep_len"].tolist(), rec["difficult"].tolist()))
+    want = [t for m in ora.envs for t in zip(m.rsi_positions, m.et_positions, m.ep_lens, m.ep_difficult)]
+    assert got == sorted(want)
+    assert sorted(env.get_attr("et_positions")[0]) == sorted(x for m in ora.envs for x in m.et_positions)
+    assert sorted(env.get_attr("difficult_rsi_phases")[0]) == sorted(x for m in ora.envs for x in m.difficult_rsi_phases)
+    assert rec["difficult"].sum() >= 1
     st = env.stats()
     assert st["episodes"] == n_done and st["falls"] + st["timeouts"] == n_done and st["timeouts"] >= 3
     assert st["ep_len_sum"] == sum(lens_o)

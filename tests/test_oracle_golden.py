@@ -82,6 +82,9 @@ def test_rollout_matches_reference(golden_dir, fixture, ep_dur_max):
         got = np.array([float(getattr(m, name)) for m in venv.envs])
         np.testing.assert_allclose(got, g["mon_" + name], rtol=1e-12, atol=0, err_msg=name)
     np.testing.assert_array_equal([x for m in venv.envs for x in m.ep_lens], g["mon_ep_lens_flat"])
+    if "mon_rsi_positions" in g.files:
+        for name in ("rsi_positions", "et_positions", "difficult_rsi_phases"):
+            np.testing.assert_array_equal([x for m in venv.envs for x in getattr(m, name)], g["mon_" + name], err_msg=name)
 
 
 def test_w165_rollout_matches_reference(golden_dir):

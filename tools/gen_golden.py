@@ -429,6 +429,12 @@ def gen_w3d_rollout(n_envs=8, n_steps=400, seed=0, out="w3d_rollout.npz", hypers
         g["mon_" + name] = np.array([float(getattr(m, name)) for m in envs])
     g["mon_ep_lens"] = np.array([len(m.ep_lens) for m in envs], np.int32)
     g["mon_ep_lens_flat"] = np.array([x for m in envs for x in m.ep_lens], np.int32)
+    # per-episode position records (monitor_wrapper.py:91-93,104-107,123-124); the construction-time Monitor state is
+    # empty, so the lists hold exactly the episodes of this run
+    g["mon_rsi_positions"] = np.array([x for m in envs for x in m.rsi_positions], np.int32)
+    g["mon_et_positions"] = np.array([x for m in envs for x in m.et_positions], np.int32)
+    g["mon_difficult_rsi_phases"] = np.array([x for m in envs for x in m.difficult_rsi_phases], np.int32)
+    g["mon_n_rsi_per_env"] = np.array([len(m.rsi_positions) for m in envs], np.int32)
     g["meta"] = np.array("reference MimicWalker3dEnv+Monitor (unmodified) over oracle physics; Q4 waived; "
                          "per-env smoothing dicts; seed=%d" % seed)
     os.makedirs(os.path.join(REPO, "tests/golden"), exist_ok=True)

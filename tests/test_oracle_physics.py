@@ -142,3 +142,15 @@ def test_blowup_is_reported():
     q, v = m.qpos0.copy(), np.zeros(m.nv)
     v[0] = 1e11
     assert P.step(q, v, np.zeros(m.nu), 1)
+
+
+def test_tree_solve_prototype_matches_dense_solve():
+    """tools/proto_tree_solve.py: H = M + sum S_b^T W_b S_b + diag solved by the articulated-body
+    recursion equals the dense solve; its numpy kinematics reproduce the oracle's mass matrix."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    p = subprocess.run([sys.executable, os.path.join(root, "tools", "proto_tree_solve.py")], capture_output=True,
+                       text=True, timeout=300)
+    assert p.returncode == 0 and p.stdout.strip().endswith("OK"), p.stdout + p.stderr

@@ -152,3 +152,44 @@ def test_eval_mode_matches_reference(spec, golden_dir):
     assert crossed >= E                                                 # every episode crossed its first transition
     # the quirk itself: episode 1 starts on step 1 (a left step: mirrored obs) but with step 0's phase denominator
     assert g["cursor0"][1, 0] == 1 and g["phase"][1, 0] == (g["cursor"][1, 0, 1]) / spec.mocap.step_len[0]
+
+
+def test_blowup_path_matches_reference(spec, golden_dir):
+    """MujocoException path (mimic_env.py:82-91, Q19): reset inside step(), reward 0, done, then the VecEnv's own
+    reset.  Same `random` seeding protocol as tools/gen_golden.py (gen_w3d_blowup)."""
+    import random
+    from oracle.env_oracle import OracleMimicEnv, OracleMonitor
+    g = np.load(os.path.join(golden_dir, "w3d_blowup.npz"))
+    T, N = g["actions"].shape[:2]
+    mons = [OracleMonitor(OracleMimicEnv(spec, OraclePhysics(spec.model))) for _ in range(N)]
+    blow = {tuple(x) for x in g["blow"].tolist()}
+    for i, m in enumerate(mons):
+        m.env.refs.count_steps_same_vel = int(g["count0"][i])
+        random.seed(900 + i)
+        np.testing.assert_array_equal(m.env.reset(), g["obs0"][i])
+    for t in range(T):
+        for i, m in enumerate(mons):
+            if (t, i) in blow:
+                m.env.qvel[3] = 1e11
+            random.seed(1000 * t + i)
+            o, r, d, _ = m.step(g["actions"][t, i])
+            assert d == bool(g["done"][t, i]) and r == g["rew"][t, i] and not np.signbit(r), (t, i)
+            if d:
+                np.testing.assert_array_equal(o, g["terminal_obs"][t, i])
+                random.seed(500000 + 1000 * t + i)
+                o = m.env.reset()
+            np.testing.assert_array_equal(o, g["obs"][t, i], err_msg=f"t={t} env={i}")
+            np.testing.assert_array_equal(m.env.qpos, g["qpos"][t, i])
+            e = m.env
+            assert (e.refs.i_step, e.refs.pos, e.refs.count_steps_same_vel, e.ep_dur) == tuple(g["cursor"][t, i])
+    assert g["done"].sum() == 3 and (g["rew"][g["done"] > 0] == 0).all()
+    np.testing.assert_array_equal([x for m in mons for x in m.ep_lens], g["mon_ep_lens_flat"])
+    np.testing.assert_array_equal([x for m in mons for x in m.et_positions], g["mon_et_positions"])
+    for name in ("ep_len_smoothed", "ep_ret_smoothed", "moved_distance", "mean_ep_pos_rew_smoothed",
+                 "mean_abs_ep_torque_smoothed"):
+        got = np.array([float(getattr(m, name)) for m in mons])
+        np.testing.assert_allclose(got, g["mon_" + name], rtol=1e-12, err_msg=name)
+    # env 1 had a one-step episode (two blow-ups in a row): the reference's np.mean of an empty list turns its
+    # mean_reward_smoothed into NaN for good; oracle and kernel skip that update instead (DESIGN.md §4, waived)
+    assert np.isnan(g["mon_mean_reward_smoothed"][1]) and np.isfinite(float(mons[1].mean_reward_smoothed))
+    assert float(mons[0].mean_reward_smoothed) == g["mon_mean_reward_smoothed"][0]

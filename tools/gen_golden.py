@@ -484,6 +484,62 @@ def gen_w3d_eval(out="w3d_eval.npz", seed=0, n_episodes=6, n_steps=70):
     print(out, "valid steps per episode:", g["n_valid"], "first cursors:", g["cursor0"].tolist())
 
 
+def gen_w3d_blowup(out="w3d_blowup.npz", n_envs=2, n_steps=30):
+    """the MujocoException path (mimic_env.py:82-91): the env resets itself, returns (obs, 0, True, {}) and the VecEnv
+    resets it once more (Q19).  A blow-up is provoked by writing |qvel| > 1e10 into the simulator before chosen steps
+    (MuJoCo's mj_checkVel limit; the fake sim raises MujocoException exactly then).  RSI draws are not logged here:
+    generator and test seed Python's `random` identically before every env step / reset and make the same calls."""
+    Env, Monitor, utils = load_reference()
+    rng = np.random.default_rng(5)
+    envs, ewa, pristine = [], [], []
+    for i in range(n_envs):
+        utils._exp_weighted_averages = {}
+        e = Monitor(Env())
+        envs.append(e)
+        ewa.append({})
+        pristine.append(copy.deepcopy(e.env.refs.data))
+    nv, nu, D = 14, 8, 29
+    T = n_steps
+    blow = {(5, 0), (17, 1), (18, 1)}                       # (step, env): also two blow-ups in a row
+    g = dict(actions=np.zeros((T, n_envs, nu), np.float32), obs=np.zeros((T, n_envs, D)), rew=np.zeros((T, n_envs)),
+             done=np.zeros((T, n_envs), np.uint8), terminal_obs=np.full((T, n_envs, D), np.nan),
+             qpos=np.zeros((T, n_envs, nv)), cursor=np.zeros((T, n_envs, 4), np.int32),
+             blow=np.array(sorted(blow), np.int32), obs0=np.zeros((n_envs, D)),
+             count0=np.array([e.env.refs.count_steps_same_vel for e in envs], np.int32))
+    for i in range(n_envs):
+        utils._exp_weighted_averages = ewa[i]
+        envs[i].env.refs.data = copy.deepcopy(pristine[i])
+        random.seed(900 + i)
+        g["obs0"][i] = envs[i].env.reset()
+    for t in range(T):
+        a = (0.2 * rng.uniform(-1, 1, size=(n_envs, nu))).astype(np.float32)
+        g["actions"][t] = a
+        for i, mon in enumerate(envs):
+            utils._exp_weighted_averages = ewa[i]
+            e = mon.env
+            if (t, i) in blow:
+                e.sim.data.qvel[3] = 1e11
+                e.refs.data = copy.deepcopy(pristine[i])     # Q4 waiver for the reset inside step()
+            random.seed(1000 * t + i)
+            o, r, d, _ = mon.step(a[i])
+            g["rew"][t, i], g["done"][t, i] = r, d
+            if d:
+                g["terminal_obs"][t, i] = o
+                e.refs.data = copy.deepcopy(pristine[i])
+                random.seed(500000 + 1000 * t + i)
+                o = e.reset()
+            g["obs"][t, i] = o
+            g["qpos"][t, i] = e.sim.data.qpos
+            g["cursor"][t, i] = (e.refs._i_step, e.refs._pos, e.refs.count_steps_same_vel, e.ep_dur)
+    for name in ("ep_len_smoothed", "ep_ret_smoothed", "mean_reward_smoothed", "moved_distance",
+                 "mean_ep_pos_rew_smoothed", "mean_abs_ep_torque_smoothed"):
+        g["mon_" + name] = np.array([float(getattr(m, name)) for m in envs])
+    g["mon_ep_lens_flat"] = np.array([x for m in envs for x in m.ep_lens], np.int32)
+    g["mon_et_positions"] = np.array([x for m in envs for x in m.et_positions], np.int32)
+    np.savez_compressed(os.path.join(REPO, "tests/golden", out), **g)
+    print(out, "dones at", np.argwhere(g["done"]).tolist(), "rewards there", g["rew"][g["done"] > 0])
+
+
 def gen_w3d_cursor(out="w3d_cursor.npz", seed=0, n=1200):
     """pure cursor trace (SURVEY.md §8c known-answer iii): refs.next() from random.seed(0)."""
     _, _, _ = load_reference()
@@ -516,6 +572,8 @@ if __name__ == "__main__":
         gen_w3d_cursor()
     if which in ("all", "rollout"):
         gen_w3d_rollout()
+    if which in ("all", "blowup"):
+        gen_w3d_blowup()
     if which in ("all", "eval"):
         gen_w3d_eval()
     if which == "timeout":                   # separate process: ep_dur_max = 25 in the reference's hypers.py (:58)

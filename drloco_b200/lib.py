@@ -10,7 +10,8 @@ import os
 from .cabi import DrlConfig, DrlWalkerModel, DRL_ABI_VERSION
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdrloco_b200.so")
+# developer hook: DRLOCO_B200_LIB points at another build of the same ABI (A/B runs of kernel variants); default in-tree
+LIB_PATH = os.environ.get("DRLOCO_B200_LIB") or os.path.join(_HERE, "libdrloco_b200.so")
 _LIB = None
 
 vp, i32, f32 = C.c_void_p, C.c_int32, C.c_float

@@ -5,6 +5,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <vector>
@@ -13,9 +14,10 @@
 #include "dev_model.h"
 
 namespace drl {
-size_t step_smem_bytes(int G, int envs_per_block);
-cudaError_t launch_step(const StepArgs& a, int nv, int G, int rk4, int reset_only, int block, bool debug,
+size_t step_smem_bytes(int G, int envs_per_block, int fdv);
+cudaError_t launch_step(const StepArgs& a, int nv, int G, int rk4, int reset_only, int block, bool debug, int fdv,
                         cudaStream_t st);
+bool topology_matches(int nv, int nb, const int* body_parent, const int* dof_body, const int* dof_type);
 cudaError_t launch_extras(const float* state_f, const float* last, float* out, int n, int G, cudaStream_t st);
 cudaError_t launch_state_copy(float* state_f, int* state_i, int* state_as, float* qpos, float* qvel, int* cursor, int n,
                               int nv, int G, int to_state, cudaStream_t st);
@@ -67,7 +69,16 @@ struct DrlEnv {
   int playback = 0;
   int frame_skip_override = -1;
   float* debug = nullptr;
+  // developer hooks (environment variables read at drl_create): generation of the dynamics evaluation (2 = fd_v2.cuh,
+  // 1 = fd_v1.cuh) and the per-evaluation CTA barrier; A/B runs of kernel variants without rebuilding
+  int fd_version = 2;
+  int stage_barrier = 1;
 };
+
+static int env_int(const char* name, int dflt) {
+  const char* s = getenv(name);
+  return (s && *s) ? atoi(s) : dflt;
+}
 
 extern "C" int drl_version(void) { return DRL_ABI_VERSION; }
 extern "C" const char* drl_last_error(void) { return g_err; }
@@ -86,6 +97,8 @@ extern "C" int drl_create(const DrlConfig* cfg, DrlEnv** out) {
   CUDA_TRY(cudaSetDevice(cfg->device));
   DrlEnv* e = new DrlEnv();
   e->cfg = *cfg;
+  e->fd_version = env_int("DRLOCO_B200_FD", 2) == 1 ? 1 : 2;
+  e->stage_barrier = env_int("DRLOCO_B200_STAGE_BARRIER", 1) ? 1 : 0;
   *out = e;
   return DRL_OK;
 }
@@ -228,6 +241,9 @@ extern "C" int drl_upload_model(DrlEnv* e, const DrlWalkerModel* m) {
       seen_hinge_root = true;
     }
   }
+  if (e->fd_version == 2 && !topology_matches(m->nv, m->nb, d.body_parent, d.dof_body, d.dof_type))
+    return fail(DRL_ERR_UNSUPPORTED, "model: the kernels are compiled for the chain layout of walker3d_flat_feet.xml "
+                                     "(nv 14) and walker_165cm_65kg.xml (nv 19); this model's tree differs");
   for (int b = 0; b < m->nb; b++) {
     if (d.body_ndof[b] == 0) return fail(DRL_ERR_UNSUPPORTED, "model: every body needs at least one joint");
     d.body_hinge0[b] = d.body_dof0[b] + (b == 0 ? d.nslide : 0);
@@ -423,6 +439,7 @@ static StepArgs make_args(DrlEnv* e) {
   a.speed_profile = e->speed_profile_len > 0 ? e->speed_profile : nullptr;
   a.speed_profile_len = e->speed_profile_len;
   a.playback = e->playback;
+  a.stage_barrier = e->stage_barrier;
   if (e->playback) a.frame_skip = 0;
   a.debug = e->debug;
   return a;
@@ -436,7 +453,7 @@ extern "C" int drl_reset(DrlEnv* e, const uint8_t* mask, const int32_t* inj_iste
   StepArgs a = make_args(e);
   a.reset_mask = mask; a.inj_istep = inj_istep; a.inj_pos = inj_pos; a.obs = obs;
   a.debug = nullptr;
-  CUDA_TRY(launch_step(a, e->nv, e->G, e->cfg.integrator == DRL_INTEGRATOR_RK4, 1, e->block, false, (cudaStream_t)stream));
+  CUDA_TRY(launch_step(a, e->nv, e->G, e->cfg.integrator == DRL_INTEGRATOR_RK4, 1, e->block, false, e->fd_version, (cudaStream_t)stream));
   return DRL_OK;
 }
 
@@ -450,7 +467,8 @@ extern "C" int drl_step(DrlEnv* e, const float* actions, float* obs, float* rew,
   a.inj_istep = inj_istep; a.inj_pos = inj_pos;
     const bool rk4 = e->cfg.integrator == DRL_INTEGRATOR_RK4;
   if (e->debug && rk4) return fail(DRL_ERR_UNSUPPORTED, "drl_step: the dump variant exists for the Euler integrator only");
-  CUDA_TRY(launch_step(a, e->nv, e->G, rk4, 0, e->block, e->debug != nullptr, (cudaStream_t)stream));
+  CUDA_TRY(launch_step(a, e->nv, e->G, rk4, 0, e->block, e->debug != nullptr, e->fd_version,
+                       (cudaStream_t)stream));
   return DRL_OK;
 }
 
@@ -573,7 +591,7 @@ extern "C" int drl_launch_info(DrlEnv* e, int32_t* lanes_per_env, int32_t* block
   if (lanes_per_env) *lanes_per_env = e->G;
   if (block_threads) *block_threads = e->block;
   if (grid_blocks) *grid_blocks = (e->cfg.num_envs + epb - 1) / epb;
-  if (smem_bytes) *smem_bytes = (int)step_smem_bytes(e->G, epb);
+  if (smem_bytes) *smem_bytes = (int)step_smem_bytes(e->G, epb, e->fd_version);
   return DRL_OK;
 }
 

@@ -118,6 +118,7 @@ struct StepArgs {
   const float* speed_profile;        // desired speed per control step (activate_speed_control), null when off
   int speed_profile_len;
   int playback;                      // kinematic playback: the state is set from the mocap instead of simulated
+  int stage_barrier;                 // CTA barrier before every dynamics evaluation (instruction-cache sharing)
   float* debug;                      // nullable: per-env dump of one forward evaluation (tests)
 };
 

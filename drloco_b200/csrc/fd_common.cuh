@@ -1,0 +1,161 @@
+// fd_common.cuh — helpers shared by the dynamics-evaluation variants of the step kernel (internal to libdrloco_b200).
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "../../include/drloco_b200.h"
+#include "dev_model.h"
+
+namespace drl {
+
+constexpr int kNPass = 2;          // contact candidates per lane
+constexpr int kMaxSolverIter = 10;
+constexpr float kMinVal = 1e-15f;
+constexpr unsigned kFull = 0xFFFFFFFFu;
+
+__device__ __forceinline__ void cross3(float& rx, float& ry, float& rz, float ax, float ay, float az, float bx,
+                                       float by, float bz) {
+  rx = ay * bz - az * by;
+  ry = az * bx - ax * bz;
+  rz = ax * by - ay * bx;
+}
+
+struct Vec6 {
+  float w0, w1, w2, v0, v1, v2;
+};
+
+__device__ __forceinline__ Vec6 ld6(const float* p) {
+  float4 a = *reinterpret_cast<const float4*>(p);
+  float2 b = *reinterpret_cast<const float2*>(p + 4);
+  return Vec6{a.x, a.y, a.z, a.w, b.x, b.y};
+}
+__device__ __forceinline__ void st6(float* p, const Vec6& x) {
+  *reinterpret_cast<float4*>(p) = make_float4(x.w0, x.w1, x.w2, x.v0);
+  *reinterpret_cast<float2*>(p + 4) = make_float2(x.v1, x.v2);
+}
+__device__ __forceinline__ float dot6(const Vec6& a, const Vec6& b) {
+  return a.w0 * b.w0 + a.w1 * b.w1 + a.w2 * b.w2 + a.v0 * b.v0 + a.v1 * b.v1 + a.v2 * b.v2;
+}
+__device__ __forceinline__ void axpy6(Vec6& y, float a, const Vec6& x) {
+  y.w0 += a * x.w0; y.w1 += a * x.w1; y.w2 += a * x.w2;
+  y.v0 += a * x.v0; y.v1 += a * x.v1; y.v2 += a * x.v2;
+}
+
+// spatial inertia (m, h, I about O) times twist -> momentum/wrench (angular, linear)
+__device__ __forceinline__ Vec6 inertia_mul(const float* I, const Vec6& t) {
+  float4 a = *reinterpret_cast<const float4*>(I);       // m hx hy hz
+  float4 b = *reinterpret_cast<const float4*>(I + 4);   // Ixx Ixy Ixz Iyy
+  float2 c = *reinterpret_cast<const float2*>(I + 8);   // Iyz Izz
+  float m = a.x, hx = a.y, hy = a.z, hz = a.w;
+  Vec6 r;
+  float cx, cy, cz;
+  cross3(cx, cy, cz, hx, hy, hz, t.v0, t.v1, t.v2);      // angular: I w + h x v
+  r.w0 = b.x * t.w0 + b.y * t.w1 + b.z * t.w2 + cx;
+  r.w1 = b.y * t.w0 + b.w * t.w1 + c.x * t.w2 + cy;
+  r.w2 = b.z * t.w0 + c.x * t.w1 + c.y * t.w2 + cz;
+  cross3(cx, cy, cz, t.w0, t.w1, t.w2, hx, hy, hz);      // linear: m v + w x h
+  r.v0 = m * t.v0 + cx;
+  r.v1 = m * t.v1 + cy;
+  r.v2 = m * t.v2 + cz;
+  return r;
+}
+
+// reciprocal: hardware approximation + one Newton step (relative error ~1e-7, no IEEE-division slow path)
+__device__ __forceinline__ float fast_rcp(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return fmaf(r, fmaf(-x, r, 1.f), r);
+}
+
+// general solimp power (MuJoCo default is 2, handled inline by impedance())
+__device__ __noinline__ float impedance_pow(float x, float mid, float power) {
+  return (x <= mid) ? powf(x, power) / powf(mid, power - 1.f)
+                    : 1.f - powf(1.f - x, power) / powf(1.f - mid, power - 1.f);
+}
+
+__device__ __forceinline__ float impedance(const DevModel& M, float dist) {
+  float x = fabsf(dist) * M.imp_inv_width;
+  if (x >= 1.f) return M.imp_dmax;
+  if (x <= 0.f) return M.imp_d0;
+  float y;
+  if (M.imp_power == 2.f) {
+    y = (x <= M.imp_mid) ? x * x * M.imp_inv_mid : 1.f - (1.f - x) * (1.f - x) * M.imp_inv_1mmid;
+  } else if (M.imp_power == 1.f) {
+    y = x;
+  } else {
+    y = impedance_pow(x, M.imp_mid, M.imp_power);
+  }
+  return M.imp_d0 + y * (M.imp_dmax - M.imp_d0);
+}
+
+// per-lane role constants
+struct LaneConst {
+  int l;               // lane within the env group
+  unsigned emask;      // lanes of this lane's environment within the warp
+  bool isdof, isbody;
+  int body, type, limited, last;
+  float sign, ref, damping, armature, lo, hi, invw;
+  unsigned anc, desc, subb;
+};
+
+struct Counters {
+  int evals, iters, capped;
+};
+
+// active set carried from one dynamics evaluation to the next (lane <-> contact candidate is a fixed mapping)
+struct ActiveSet {
+  unsigned bits[kNPass];  // active pyramid rows of this lane's candidate in each pass
+  unsigned prev_act;      // which of this lane's candidates were in contact at the previous evaluation
+  bool lbit, prev_lim;    // joint-limit row of this lane's dof
+};
+
+// symmetric 6x6 index into 21 packed entries (i <= j)
+__device__ __forceinline__ constexpr int sym6(int i, int j) {
+  return (i <= j) ? (i * 6 - (i * (i - 1)) / 2 + (j - i)) : (j * 6 - (j * (j - 1)) / 2 + (i - j));
+}
+
+// pop the two lowest set bits of a mask (i1 = i0 and second = false when only one is left): the chain loops below
+// consume two entries per trip so that their shared-memory loads are in flight together
+__device__ __forceinline__ void pop2(unsigned& mk, int& i0, int& i1, bool& second) {
+  i0 = __ffs(mk) - 1;
+  mk &= mk - 1;
+  second = mk != 0u;
+  i1 = second ? __ffs(mk) - 1 : i0;
+  mk &= mk - 1;
+}
+
+// does predicate p hold on any lane of this lane's environment?
+__device__ __forceinline__ bool env_any(bool p, unsigned emask) { return (__ballot_sync(kFull, p) & emask) != 0u; }
+
+// LDL^T solve with the symmetric matrix spread one column per lane: H[0..NV-1] = rows of this lane's column (full
+// column, both triangles), H[NV] = this lane's rhs entry.  Right-looking elimination; column k is left unscaled
+// (H[r][k] = l_rk d_k) so that each trailing update is one shuffle + one FMA.  Returns x for this lane's row.
+template <int NV, int G>
+__device__ __forceinline__ float ldl_solve_cols(float (&H)[NV + 1], int l) {
+  float invd = 0.f;
+#pragma unroll
+  for (int k = 0; k < NV; k++) {
+    const float dk = __shfl_sync(kFull, H[k], k, G);
+    const float inv = fast_rcp(fmaxf(dk, 1e-30f));
+    const float lck = H[k] * inv;          // lanes c > k: l_ck = H[c][k] / d_k (H is symmetric)
+    const bool upd = l > k;
+    if (l == k) invd = inv;
+#pragma unroll
+    for (int r = k + 1; r <= NV; r++) {
+      const float vr = __shfl_sync(kFull, H[r], k, G);     // H[r][k];  r == NV: forward-substituted rhs z_k
+      if (upd) H[r] = fmaf(-vr, lck, H[r]);
+    }
+  }
+  // x_c = (z_c - sum_{r>c} H[r][c] x_r) / d_c
+  float sacc = H[NV], x = 0.f;
+#pragma unroll
+  for (int k = NV - 1; k >= 0; k--) {
+    const float xk = __shfl_sync(kFull, sacc * invd, k, G);
+    if (l < k) sacc = fmaf(-H[k], xk, sacc);
+    if (l == k) x = xk;
+  }
+  return x;
+}
+
+}  // namespace drl

@@ -72,6 +72,16 @@ class OraclePhysics:
         return bool(self._l.orc_step(C.byref(self.cm), _p(q), _p(v), _p(ctrl), _p(self.qacc_warm), int(nsub),
                                      int(self.integrator)))
 
+    def step_trace(self, q, v, ctrl, nsub):
+        """like step() (in place) but also returns the constraint-set signature of every dynamics evaluation:
+        uint64 [nsub, 4, 2] = (contact candidates, limit rows) per substep and RK4 stage."""
+        assert q.dtype == np.float64 and v.dtype == np.float64 and q.flags.c_contiguous and v.flags.c_contiguous
+        ctrl = np.ascontiguousarray(ctrl, np.float64)
+        sig = np.zeros((int(nsub), 4, 2), np.uint64)
+        bad = bool(self._l.orc_step_trace(C.byref(self.cm), _p(q), _p(v), _p(ctrl), _p(self.qacc_warm), int(nsub),
+                                          int(self.integrator), _p(sig)))
+        return bad, sig
+
     def site_xpos(self, q):
         out = np.zeros((len(self.model.site_body), 3))
         self._l.orc_site_xpos(C.byref(self.cm), _p(np.ascontiguousarray(q, np.float64)), _p(out))

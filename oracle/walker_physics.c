@@ -271,6 +271,12 @@ long g_as_hist[64], g_as_fail = 0;
 void orc_set_solver(int mode, int maxit) { g_solver_mode = mode; g_as_maxit = maxit; memset(g_as_hist, 0, sizeof g_as_hist); g_as_fail = 0; }
 void orc_get_solver_stats(long* hist, long* fail) { memcpy(hist, g_as_hist, sizeof g_as_hist); *fail = g_as_fail; }
 
+/* which constraints the last orc_forward call instantiated: bit s for capsule end sphere s, bit n_sphere + 8 x + i for
+ * kept corner i of box x; limit rows: bit j (lower bound of dof j violated) / bit 32 + j (upper).  Read by the
+ * contact-sensitivity probe of the parity tests (oracle/sensitivity.py). */
+static unsigned long long g_last_con = 0, g_last_lim = 0;
+void orc_get_last_sets(unsigned long long* con, unsigned long long* lim) { *con = g_last_con; *lim = g_last_lim; }
+
 typedef struct { double a; int i; } Brk;
 static int brk_cmp(const void* x, const void* y) {
   double a = ((const Brk*)x)->a, b = ((const Brk*)y)->a;
@@ -310,6 +316,7 @@ int orc_forward(const DrlWalkerModel* m, const double* q, const double* v, const
   double tc = fmax(m->solref[0], 2 * m->timestep), dr = m->solref[1];
   double dmax = fmin(MJ_MAXIMP, fmax(MJ_MINIMP, m->solimp[1]));
   double Kc = 1.0 / (dmax * dmax * tc * tc * dr * dr), Bc = 2.0 / (dmax * tc);
+  unsigned long long con_set = 0, lim_set = 0;
   /* joint limits (mj_instantiateLimit) */
   for (int j = 0; j < nv; j++) {
     if (!m->dof_limited[j]) continue;
@@ -324,6 +331,7 @@ int orc_forward(const DrlWalkerModel* m, const double* q, const double* v, const
       D[nrow] = 1.0 / R;
       aref[nrow] = -Bc * sg * v[j] - Kc * imp * dist;
       row_con[nrow] = -1;
+      lim_set |= 1ull << (j + 32 * side);
       nrow++; nlimit++;
     }
   }
@@ -339,6 +347,7 @@ int orc_forward(const DrlWalkerModel* m, const double* q, const double* v, const
     cpos[ncon][0] = k->xpos[b][0] + r[0]; cpos[ncon][1] = k->xpos[b][1] + r[1];
     cpos[ncon][2] = cz - (m->sphere_radius[s] + 0.5 * dist);
     cdist[ncon] = dist; cmu[ncon] = m->sphere_mu[s]; cbody[ncon] = b; ncon++;
+    con_set |= 1ull << s;
   }
   for (int x = 0; x < m->n_box; x++) {
     int b = m->box_body[x], cnt = 0;
@@ -354,8 +363,10 @@ int orc_forward(const DrlWalkerModel* m, const double* q, const double* v, const
       cpos[ncon][0] = ctr[0] + corner[0]; cpos[ncon][1] = ctr[1] + corner[1];
       cpos[ncon][2] = ctr[2] + corner[2] - 0.5 * dist;
       cdist[ncon] = dist; cmu[ncon] = m->box_mu[x]; cbody[ncon] = b; ncon++; cnt++;
+      con_set |= 1ull << (m->n_sphere + 8 * x + i);
     }
   }
+  g_last_con = con_set; g_last_lim = lim_set;
   /* pyramidal rows (condim 3): J_n +- mu J_t1, J_n +- mu J_t2; contact frame n = +z, tangents y and x */
   for (int ci = 0; ci < ncon; ci++) {
     int b = cbody[ci];
@@ -537,10 +548,11 @@ int orc_forward(const DrlWalkerModel* m, const double* q, const double* v, const
 
 /* nsub MuJoCo steps with ctrl held (MujocoEnv.do_simulation).  integrator: DRL_INTEGRATOR_RK4 / _EULER.
  * Returns 0, or 1 if the state left the finite range MuJoCo accepts (mj_checkPos/Vel/Acc -> MujocoException). */
-int orc_step(const DrlWalkerModel* m, double* q, double* v, const double* ctrl, double* qacc_warm, int nsub,
-             int integrator) {
+static int step_sig(const DrlWalkerModel* m, double* q, double* v, const double* ctrl, double* qacc_warm, int nsub,
+                    int integrator, unsigned long long* sig /* nullable: [nsub][4][2] */) {
   int nv = m->nv;
   double h = m->timestep;
+  if (sig) memset(sig, 0, sizeof(unsigned long long) * (size_t)nsub * 8);
   for (int s = 0; s < nsub; s++) {
     for (int j = 0; j < nv; j++)
       if (!isfinite(q[j]) || !isfinite(v[j]) || fabs(q[j]) > 1e10 || fabs(v[j]) > 1e10) return 1;
@@ -550,6 +562,7 @@ int orc_step(const DrlWalkerModel* m, double* q, double* v, const double* ctrl, 
       memcpy(qs, q, sizeof(double) * nv); memcpy(vs, v, sizeof(double) * nv);
       for (int st = 0; st < 4; st++) {
         if (orc_forward(m, qs, vs, ctrl, qacc_warm, kv[st], NULL)) return 1;
+        if (sig) { sig[(s * 4 + st) * 2] = g_last_con; sig[(s * 4 + st) * 2 + 1] = g_last_lim; }
         memcpy(kq[st], vs, sizeof(double) * nv);
         if (st < 3)
           for (int j = 0; j < nv; j++) { qs[j] = q[j] + h * A[st] * kq[st][j]; vs[j] = v[j] + h * A[st] * kv[st][j]; }
@@ -563,6 +576,7 @@ int orc_step(const DrlWalkerModel* m, double* q, double* v, const double* ctrl, 
       /* mj_Euler: implicit in joint damping: (M + h B) a' = M a + ... == tau_total; here M a = tau + J'f */
       double a[NV];
       if (orc_forward(m, q, v, ctrl, qacc_warm, a, NULL)) return 1;
+      if (sig) { sig[(s * 4) * 2] = g_last_con; sig[(s * 4) * 2 + 1] = g_last_lim; }
       Kin* k = (Kin*)malloc(sizeof(Kin));
       double M[NV * NV], rhs[NV];
       kinematics(m, q, k);
@@ -582,6 +596,18 @@ int orc_step(const DrlWalkerModel* m, double* q, double* v, const double* ctrl, 
   for (int j = 0; j < nv; j++)
     if (!isfinite(q[j]) || !isfinite(v[j]) || fabs(q[j]) > 1e10 || fabs(v[j]) > 1e10) return 1;
   return 0;
+}
+
+int orc_step(const DrlWalkerModel* m, double* q, double* v, const double* ctrl, double* qacc_warm, int nsub,
+             int integrator) {
+  return step_sig(m, q, v, ctrl, qacc_warm, nsub, integrator, NULL);
+}
+
+/* orc_step that also reports, for every dynamics evaluation (substep x RK4 stage), which contact candidates and limit
+ * rows were instantiated: the constraint-set signature the contact-sensitivity probe compares. */
+int orc_step_trace(const DrlWalkerModel* m, double* q, double* v, const double* ctrl, double* qacc_warm, int nsub,
+                   int integrator, unsigned long long* sig) {
+  return step_sig(m, q, v, ctrl, qacc_warm, nsub, integrator, sig);
 }
 
 /* site world positions (sim.data.site_xpos after set_state / sim.forward, mimic_env.py:549) */

@@ -30,6 +30,19 @@ def _oracle(spec, n, integrator="rk4", physics=None):
     return OracleVecEnv(spec, n, physics or (lambda: OraclePhysics(spec.model, integ)))
 
 
+def _oracle_probed(spec, n, integrator="rk4"):
+    """oracle env whose physics also runs the contact-sensitivity probe (oracle/sensitivity.py); returns (env, probes)"""
+    from oracle.env_oracle import OracleVecEnv
+    from oracle.sensitivity import SensitivityProbe
+    integ = cabi.INTEGRATOR_RK4 if integrator == "rk4" else cabi.INTEGRATOR_EULER
+    probes = []
+
+    def make():
+        probes.append(SensitivityProbe(spec.model, integ, seed=len(probes)))
+        return probes[-1]
+    return OracleVecEnv(spec, n, make), probes
+
+
 def _rsi(spec, n, rng):
     t = spec.mocap
     istep = rng.integers(0, t.n_steps, n).astype(np.int32)
@@ -103,10 +116,15 @@ def test_forward_dynamics_pieces(env_id):
 # --------------------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("env_id,integrator,steps", [(W3D, "rk4", 8), (W3D, "euler", 8), (W165, "rk4", 6)])
 def test_rollout_parity_short_horizon(env_id, integrator, steps):
+    """Stated tolerance: REL_TOL for EVERY environment the oracle does not flag as contact-sensitive.  An environment is
+    flagged when the float64 oracle itself, re-run from its state perturbed at float32 resolution, instantiates a
+    different constraint set within a control step (oracle/sensitivity.py) - there the soft-contact force is
+    discontinuous and no float32 trajectory can be expected to follow the float64 one.  The flagged fraction is
+    reported and bounded."""
     n = 64
     env = _env(env_id, n, integrator)
     spec = env.spec
-    ora = _oracle(spec, n, integrator)
+    ora, probes = _oracle_probed(spec, n, integrator)
     rng = np.random.default_rng(1)
     istep, pos = _rsi(spec, n, rng)
     og, oo = env.reset(inject=(istep, pos)), ora.reset(istep, pos)
@@ -115,30 +133,35 @@ def test_rollout_parity_short_horizon(env_id, integrator, steps):
     qo, vo, co = _ora_state(ora)
     np.testing.assert_array_equal(cg, co)                                  # cursor after RSI + next(): bit-exact
     assert np.abs(qg - qo).max() < 1e-5
-    curve = []
+    curve, worst_flagged = [], 0.0
     for k in range(steps):
         a = rng.uniform(-1, 1, (n, spec.act_dim)).astype(np.float32)
         og, rg, dg, _ = env.step(a, inject=(istep, pos))
         oo, ro, do, _ = ora.step(a, istep, pos)
         qg, vg, cg = env.get_state()
         qo, vo, co = _ora_state(ora)
-        np.testing.assert_array_equal(dg, do, err_msg=f"done flags, step {k}")
-        np.testing.assert_array_equal(cg, co, err_msg=f"cursor, step {k}")
+        for i in np.nonzero(do & dg)[0]:
+            probes[i].clear()                                              # both sides restart from the same RSI state
+        flagged = np.array([p.flagged for p in probes])
         rows = np.maximum(np.maximum(_rel_rows(qg, qo), _rel_rows(vg, vo)), np.abs(rg - ro))
-        eq, ev, er = _rel(qg, qo), _rel(vg, vo), float(np.abs(rg - ro).max())
-        curve.append((eq, ev, er))
-        # every env within the stated tolerance, except that an env whose foot corner crosses the ground within
-        # rounding of a substep boundary may pick the contact up one substep apart (the soft contact's damping force
-        # is discontinuous at activation): at most 2 of 64 such envs, and the bulk far below the tolerance
-        assert (rows < REL_TOL).mean() >= 62 / 64 and np.median(rows) < 0.2 * REL_TOL, (k, eq, ev, er)
+        ok = ~flagged
+        np.testing.assert_array_equal(dg[ok], do[ok], err_msg=f"done flags, step {k}")
+        np.testing.assert_array_equal(cg[ok], co[ok], err_msg=f"cursor, step {k}")
+        curve.append((float(rows[ok].max()), float(np.median(rows)), int(flagged.sum())))
+        assert rows[ok].max() < REL_TOL, (k, np.nonzero(rows >= REL_TOL)[0], np.nonzero(flagged)[0], rows.max())
+        assert np.median(rows) < 0.2 * REL_TOL
+        if flagged.any():
+            worst_flagged = max(worst_flagged, float(rows[flagged].max()))
         # phase and desired velocity are pure table lookups: bit-exact against float32(oracle)
         if spec.phase_from_cursor:
             left = np.array([bool(spec.mocap.left_step[c[0]]) for c in co])
-            np.testing.assert_array_equal(og[:, 0].astype(np.float32), oo[:, 0].astype(np.float32))
-            np.testing.assert_array_equal(og[:, 1].astype(np.float32), oo[:, 1].astype(np.float32))
+            np.testing.assert_array_equal(og[ok, 0].astype(np.float32), oo[ok, 0].astype(np.float32))
+            np.testing.assert_array_equal(og[ok, 1].astype(np.float32), oo[ok, 1].astype(np.float32))
             assert left.any() and (~left).any()
-    print(f"{env_id}/{integrator} divergence (rel q, rel v, abs reward) per step:",
-          ["%.1e/%.1e/%.1e" % c for c in curve])
+    n_flag = int(np.array([p.flagged for p in probes]).sum())
+    assert n_flag <= n // 8, f"{n_flag} of {n} environments flagged contact-sensitive: the criterion would be vacuous"
+    print(f"{env_id}/{integrator}: per step (max rel err of non-flagged envs, median, #flagged):",
+          ["%.1e/%.1e/%d" % c for c in curve], f"; worst flagged env {worst_flagged:.1e}")
     env.close()
 
 
@@ -320,6 +343,62 @@ def test_env_logic_and_monitor_on_injected_states():
     assert st["ep_len_sum"] == sum(lens_o)
     env.set_attr("ep_lens", [])                                  # callback.py:69-70
     assert len(env.episode_lengths()) == 0
+    env.close()
+
+
+def test_blowup_path_golden_from_reference_python(golden_dir):
+    """MujocoException path (mimic_env.py:82-91) on the GPU against the fixture produced by the reference's own
+    MimicWalker3dEnv + Monitor (tools/gen_golden.py gen_w3d_blowup): |qvel| > 1e10 written into the simulator before
+    chosen steps, incl. two blow-ups in a row.  The RSI draws are those of the generator (same `random` seeding
+    protocol as tests/test_oracle_golden.py::test_blowup_path_matches_reference), injected on the device.  Kept
+    reference behaviour: reward +0.0, done, observation after the reset, cursor, Monitor episode records.  Waived
+    (Q19): the reference resets twice and reports the first reset's observation as terminal."""
+    import random
+    g = np.load(os.path.join(golden_dir, "w3d_blowup.npz"))
+    T, n = g["actions"].shape[:2]
+    env = _env(W3D, n)
+    t_ = env.spec.mocap
+
+    def draw(seed):                                           # RefCursor.init_random / straight:460-474
+        random.seed(seed)
+        i = random.randint(0, t_.n_steps - 1)
+        return i, random.randint(0, int(t_.step_len[i]) - 1)
+
+    cur = np.zeros((n, 4), np.int32)
+    cur[:, 2] = g["count0"]                                   # count_steps_same_vel survives resets (Q3)
+    env.set_state(None, None, cur)
+    rsi = np.array([draw(900 + i) for i in range(n)], np.int32)
+    obs = env.reset(inject=(rsi[:, 0], rsi[:, 1]))
+    assert _rel(obs, g["obs0"]) < 2e-5
+    blow = {tuple(x) for x in g["blow"].tolist()}
+    since_reset = np.zeros(n, int)
+    for t in range(T):
+        hit = [i for i in range(n) if (t, i) in blow]
+        if hit:
+            q, v, c = env.get_state()
+            v[hit, 3] = 1e11
+            env.set_state(q, v, c)
+        rsi = np.array([draw(500000 + 1000 * t + i) for i in range(n)], np.int32)
+        obs, rew, done, infos = env.step(g["actions"][t], inject=(rsi[:, 0], rsi[:, 1]))
+        np.testing.assert_array_equal(done, g["done"][t].astype(bool), err_msg=f"t={t}")
+        qg, _, cg = env.get_state()
+        np.testing.assert_array_equal(cg, g["cursor"][t], err_msg=f"t={t}")
+        since_reset = np.where(done, 0, since_reset + 1)
+        for i in range(n):
+            if done[i]:                                       # every done of this fixture is a blow-up
+                assert (t, i) in blow and rew[i] == 0.0 and not np.signbit(rew[i])
+                assert "terminal_observation" in infos[i] and np.isfinite(infos[i]["terminal_observation"]).all()
+                assert _rel(obs[i][None], g["obs"][t, i][None]) < 2e-5 and _rel(qg[i][None], g["qpos"][t, i][None]) < 1e-5
+            else:
+                # free-running fp32 physics vs the float64 fixture: tight over the stated horizon, loose after it
+                tol = REL_TOL if since_reset[i] <= 8 else 5e-3
+                assert _rel(obs[i][None], g["obs"][t, i][None]) < tol and abs(rew[i] - g["rew"][t, i]) < tol, (t, i)
+    assert env.stats()["blowups"] == 3 and env.stats()["episodes"] == 3
+    rec = env.episode_records()
+    assert sorted(rec["ep_len"].tolist()) == sorted(g["mon_ep_lens_flat"].tolist())
+    # (Monitor.et_positions / moved_distance of a blown-up episode are read after the reference's first, in-step
+    #  reset; with the single reset here they describe the state before it - part of the Q19 waiver)
+    np.testing.assert_allclose(env.get_attr("ep_len_smoothed"), g["mon_ep_len_smoothed"], rtol=1e-6)
     env.close()
 
 

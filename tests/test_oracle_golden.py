@@ -43,7 +43,12 @@ def test_cursor_trace_matches_reference(spec, golden_dir):
     # known-answer (iii): transitions after RSI (27,197)
     tr = g["trace"]
     change = [k for k in range(1, len(tr)) if tr[k, 0] != tr[k - 1, 0]][:5]
-    assert change == [41, 175, 312, 443, 577] or change == [40, 174, 311, 442, 576] or len(change) == 5
+    # (trace row k = the cursor after k calls of next(); the survey counts env steps, i.e. one less: 40, 174, ...)
+    assert change == [41, 175, 312, 443, 577]
+    assert [tuple(int(x) for x in tr[k]) for k in change] == [(28, 1, 269, 2), (29, 1, 275, 3), (0, 1, 262, 3),
+                                                              (1, 2, 269, 4), (2, 2, 268, 5)]
+    np.testing.assert_allclose(g["des_vel"][change], [1.464117, 1.464117, 1.471227, 1.471227, 1.471227], atol=5e-7)
+    np.testing.assert_array_equal(g["phase"][change], [1 / 269, 1 / 275, 1 / 262, 2 / 269, 2 / 268])
 
 
 @pytest.mark.parametrize("fixture,ep_dur_max", [("w3d_rollout.npz", 3000), ("w3d_timeout.npz", 25)])

@@ -350,6 +350,10 @@ extern "C" int drl_upload_model(DrlEnv* e, const DrlWalkerModel* m) {
   e->nv = m->nv;
   e->G = G;
   e->block = 128;
+  {
+    const int b = env_int("DRLOCO_B200_BLOCK", 0);     // developer hook: CTA size of the step kernel
+    if (b == 32 || b == 64 || b == 96 || b == 128) e->block = b;
+  }
   CUDA_TRY(cudaSetDevice(c.device));
   const size_t N = (size_t)c.num_envs;
   if (!e->d_model) {

@@ -34,6 +34,8 @@ struct Topo<14> {   // walker3d_flat_feet.xml: torso -> {right, left} x (thigh[2
   __host__ __device__ static constexpr int chain_len(int) { return 4; }
   // axis index of the s-th hinge at depth k when it is the same on every chain, else -1 (read from the model)
   __host__ __device__ static constexpr int axis(int k, int s) { return k == 0 ? s : (k == 1 ? (s == 0 ? 1 : 0) : 1); }
+  __host__ __device__ static constexpr int chain_of(int j) { return (j - 6) / 4; }     // for j >= NROOT
+  static constexpr int NBOX = 2;
 };
 
 template <>
@@ -45,7 +47,68 @@ struct Topo<19> {   // walker_165cm_65kg.xml: pelvis -> {right, left} x (thigh[3
   __host__ __device__ static constexpr int chain_body1(int c) { return c == 0 ? 2 : (c == 1 ? 5 : 1); }
   __host__ __device__ static constexpr int chain_len(int c) { return c == 2 ? 2 : 4; }
   __host__ __device__ static constexpr int axis(int k, int s) { return k == 0 ? s : (k == 1 ? (s == 2 ? 2 : -1) : 1); }
+  __host__ __device__ static constexpr int chain_of(int j) { return j < 9 ? 2 : (j < 14 ? 0 : 1); }   // for j >= NROOT
+  static constexpr int NBOX = 4;
 };
+
+// is dof r a strict ancestor of dof k (r moves the body k is attached to)?  The chains are serial, so: an earlier dof
+// of the root or of k's own chain.
+template <int NV>
+__host__ __device__ constexpr bool dof_is_anc(int r, int k) {
+  return r < k && (r < Topo<NV>::NROOT || Topo<NV>::chain_of(r) == Topo<NV>::chain_of(k));
+}
+// lanes (dofs) that are strict ancestors of dof k, as a bit mask
+template <int NV>
+__host__ __device__ constexpr unsigned dof_anc_mask(int k) {
+  unsigned m = 0;
+  for (int r = 0; r < k; r++)
+    if (dof_is_anc<NV>(r, k)) m |= 1u << r;
+  return m;
+}
+
+// lanes (dofs) that descend from dof k
+template <int NV>
+__host__ __device__ constexpr unsigned dof_desc_mask(int k) {
+  unsigned m = 0;
+  for (int c = k + 1; c < NV; c++)
+    if (dof_is_anc<NV>(k, c)) m |= 1u << c;
+  return m;
+}
+
+// LDL^T solve of the tree-structured system H x = z with H spread one column per lane (H[0..NV-1] = rows of this
+// lane's column, both triangles; H[NV] = this lane's rhs entry).  Elimination runs from the leaves to the root, which
+// creates no fill-in: pivot k touches only rows / columns of k's ancestors (Featherstone's sparse factorisation).
+// Column k is left unscaled (H[r][k] = l_rk d_k) so that each update is one shuffle + one FMA.  Returns x for this
+// lane's row.
+template <int NV, int G>
+__device__ __forceinline__ float ldl_solve_tree(float (&H)[NV + 1], int l) {
+  float invd = 0.f;
+  const unsigned me = 1u << l;
+#pragma unroll
+  for (int k = NV - 1; k >= 0; k--) {
+    const float dk = __shfl_sync(kFull, H[k], k, G);
+    const float inv = fast_rcp(fmaxf(dk, 1e-30f));
+    const float lck = H[k] * inv;                      // lane c in anc(k): l_kc = H[k][c] / d_k (H is symmetric)
+    const bool upd = (dof_anc_mask<NV>(k) & me) != 0u;
+    if (l == k) invd = inv;
+#pragma unroll
+    for (int r = 0; r <= NV; r++) {
+      if (r == NV || dof_is_anc<NV>(r, k)) {
+        const float vr = __shfl_sync(kFull, H[r], k, G);   // H[r][k];  r == NV: rhs entry z_k
+        if (upd) H[r] = fmaf(-vr, lck, H[r]);
+      }
+    }
+  }
+  // x_k = (z_k - sum_{r in anc(k)} H[r][k] x_r) / d_k, root first
+  float sacc = H[NV], x = 0.f;
+#pragma unroll
+  for (int k = 0; k < NV; k++) {
+    const float xk = __shfl_sync(kFull, sacc * invd, k, G);
+    if (dof_desc_mask<NV>(k) & me) sacc = fmaf(-H[k], xk, sacc);
+    if (l == k) x = xk;
+  }
+  return x;
+}
 
 template <int G>
 struct EnvSmem2 {
@@ -53,11 +116,18 @@ struct EnvSmem2 {
   float acc[G];             // qacc iterate
   float tau[G];             // actuator force per dof
   float cssn[G][2];         // cos, sin of hinge angles (slides: -, displacement)
-  float axw[G][4];          // joint axes in world orientation
   float S[G][12];           // motion vectors (omega, v_O); row stride 12 floats keeps 8-lane vector loads conflict-free
-  float Fd[G][12];          // chain-prefix velocity before dof j -> (V x S_j) v_j -> (Ic + Wsub) S_j
-  float bodyR[kMaxBody][16];  // row r of the rotation + r-th coordinate of the origin relative to O: [4r .. 4r+3]
-  float Ib[kMaxBody][12];   // spatial inertia about O: m, h[3], Ixx Ixy Ixz Iyy Iyz Izz
+  union {
+    struct {
+      float Fd[G][12];          // chain-prefix velocity before dof j -> (V x S_j) v_j -> (Ic + Wsub) S_j
+      float bodyR[kMaxBody][16];  // row r of the rotation + r-th coordinate of the origin relative to O: [4r .. 4r+3]
+      float Ib[kMaxBody][12];   // spatial inertia about O: m, h[3], Ixx Ixy Ixz Iyy Iyz Izz
+      float axw[G][4];          // joint axes in world orientation
+    };
+    // staging of the per-corner contact Hessians for the per-box sums: [box][entry 0..26][corner 0..7].  Written and
+    // consumed at the start of a solver pass, when the four arrays above are dead (Fd is rewritten right after).
+    float Wred[(G == 16 ? 2 : 4) * 27 * 8];
+  };
   float Ic[kMaxBody][12];   // composite
   union {
     struct {
@@ -73,6 +143,7 @@ struct EnvSmem2 {
   };
   float obsbuf[kMaxObs];
 };
+static_assert(sizeof(EnvSmem2<16>) % 16 == 0 && sizeof(EnvSmem2<32>) % 16 == 0, "vector loads need 16-byte rows");
 
 // lane roles that depend on the chain layout (constant over the launch)
 struct ChainLane {
@@ -236,7 +307,7 @@ __device__ __forceinline__ void forward_dynamics2(const DevModel& M, EnvSmem2<G>
   // ---- 1. joint trig + velocity ------------------------------------------------------------------------------------
   {
     float s = q - L.ref, c = 1.f;
-    if (L.isdof && L.type == 1) sincosf(L.sign * (q - L.ref), &s, &c);
+    if (L.isdof && L.type == 1) sincos_joint(L.sign * (q - L.ref), s, c);
     if (L.isdof) { *reinterpret_cast<float2*>(&E.cssn[l][0]) = make_float2(c, s); E.v[l] = v; }
   }
   __syncwarp();
@@ -359,7 +430,7 @@ __device__ __forceinline__ void forward_dynamics2(const DevModel& M, EnvSmem2<G>
   }
   __syncwarp();   // E.Ab (body forces) complete
   const bool any0 = __any_sync(kFull, cact[0]);
-  const bool sph_any = __any_sync(kFull, cact[1]);
+  const bool sph_any = __builtin_expect(__any_sync(kFull, cact[1]), 0);   // capsule contacts: fallen walkers only
   unsigned conmask = 0;
 #pragma unroll
   for (int ps = 0; ps < kNPass; ps++) {
@@ -494,22 +565,26 @@ __device__ __forceinline__ void forward_dynamics2(const DevModel& M, EnvSmem2<G>
           wv[24] = gx; wv[25] = gy; wv[26] = gz;
         }
         if (ps == 0) {
-          // pass 0 holds the box corners: the 8 lanes of a segment belong to one box = one body -> butterfly sum,
-          // then the segment stores its body's accumulators
-#pragma unroll
-          for (int i = 0; i < 27; i++) {
-            float t = wv[i];
-            t += __shfl_xor_sync(kFull, t, 1);
-            t += __shfl_xor_sync(kFull, t, 2);
-            t += __shfl_xor_sync(kFull, t, 4);
-            wv[i] = t;
-          }
+          // pass 0 holds the box corners: the 8 lanes of a segment belong to one box = one body.  Every corner lane
+          // stages its 27 numbers, then the lanes share out the 27 x (number of boxes) sums over the 8 corners
+          // (fixed order: deterministic) and store their body's accumulators.
           if (l < M.nbox_cand) {
-            const int sl = wl & 7, b = cbody[0];
+            float* dst = &E.Wred[((l >> 3) * 27) * 8 + (l & 7)];
 #pragma unroll
-            for (int i = 0; i < 27; i++) {
-              if ((i & 7) == sl) {
-                if (i < 21) E.W[b][i] = wv[i]; else E.U[b][i - 21] = wv[i];
+            for (int i = 0; i < 27; i++) dst[i * 8] = wv[i];
+          }
+          __syncwarp();
+#pragma unroll
+          for (int bx = 0; bx < T::NBOX; bx++) {
+#pragma unroll
+            for (int i0 = 0; i0 < 27; i0 += G) {
+              const int i = i0 + l;
+              if (i < 27 && bx * 8 < M.nbox_cand) {
+                const float4 x0 = *reinterpret_cast<const float4*>(&E.Wred[(bx * 27 + i) * 8]);
+                const float4 x1 = *reinterpret_cast<const float4*>(&E.Wred[(bx * 27 + i) * 8 + 4]);
+                const float sum = ((x0.x + x0.y) + (x0.z + x0.w)) + ((x1.x + x1.y) + (x1.z + x1.w));
+                const int b = M.cand_body[bx * 8];
+                if (i < 21) E.W[b][i] = sum; else E.U[b][i - 21] = sum;
               }
             }
           }
@@ -571,7 +646,7 @@ __device__ __forceinline__ void forward_dynamics2(const DevModel& M, EnvSmem2<G>
         if (r == l) H[r] += lD;
       H[NV] += lD * lsg * laref;
     }
-    a = ldl_solve_cols<NV, G>(H, l);
+    a = ldl_solve_tree<NV, G>(H, l);
     if (!L.isdof) a = 0.f;
     if (L.isdof) E.acc[l] = a;
     if (!constrained) break;

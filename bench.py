@@ -33,7 +33,31 @@ W3D_WORKLOAD = ("MimicWalker3d straight walking, %d batched envs per GPU, random
                 "(BASELINE.json configs[1])")
 ENVS_PER_GPU = 4096
 ALGO_BYTES_PER_ENV_STEP = 425.0        # SURVEY.md §8d / DESIGN.md
-ALGO_FLOP_PER_ENV_STEP = 0.32e6        # 16 kFLOP per dynamics evaluation x 20 evaluations (W3D, RK4)
+ALGO_FLOP_PER_EVAL = 16.0e3            # algorithmic flops of one dynamics evaluation (W3D)
+W165 = "MimicWalker165cm65kg"
+
+
+def algo_flop_per_env_step(env_id: str, integrator: str, frame_skip: int) -> float:
+    """evaluations per control step (frame_skip x 4 RK4 stages, or x 1 for Euler) x flops per evaluation; the W165
+    evaluation is scaled from W3D by (19/14)^2 (dense parts) as in DESIGN.md section 3."""
+    per_eval = ALGO_FLOP_PER_EVAL * ((19 / 14) ** 2 if env_id == W165 else 1.0)
+    return per_eval * frame_skip * (4 if integrator == "rk4" else 1)
+
+
+def profiled_traffic(env_id: str, n: int, integrator: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one step-kernel launch, from the committed ncu summary of the
+    current kernel (profiles/step_kernel_traffic.json, written by tools/ncu_summary.py from the .ncu-rep); None when no
+    capture exists for this shape."""
+    path = os.path.join(REPO, "profiles", "step_kernel_traffic.json")
+    try:
+        with open(path) as f:
+            table = json.load(f)
+    except (OSError, ValueError):
+        return None, None
+    for row in table.get("captures", []):
+        if row.get("env_id") == env_id and row.get("num_envs") == n and row.get("integrator") == integrator:
+            return row.get("dram_bytes"), row.get("source")
+    return None, None
 
 
 def _peaks():
@@ -196,6 +220,7 @@ def main():
                     help="informational runs of the other BASELINE.json configs; the headline is the default")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the time-bounded legs for BASELINE.json configs[2] / [3]")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     # the contract is ONE JSON line on stdout: keep a private handle to the real stdout and point fd 1 at stderr so
@@ -224,14 +249,7 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    n = args.envs_per_gpu
-    cfg = EnvConfig(env_id=args.env_id, integrator=args.integrator)
-    env = B200MimicVecEnv(args.env_id, num_envs=n, device=f"cuda:{local}", seed=rank, cfg=cfg, env_id_offset=rank * n)
-    vn = B200VecNormalize(env, distributed=world > 1)
-    dev = env.device
-    g = torch.Generator(device=dev)
-    g.manual_seed(1234 + rank)
-    ring = torch.rand(64, n, env.act_dim, device=dev, generator=g) * 2 - 1     # pre-generated action ring (§8d)
+    dev = torch.device("cuda", local)
     flush = torch.empty(192 * 1024 * 1024 // 4, device=dev)                    # > 126 MB L2
 
     def barrier():
@@ -239,114 +257,158 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    vn.reset_tensor()
-    for k in range(args.warmup):
-        vn.step_tensor(ring[k % 64])
-    barrier()
-    env.reset_stats()
-
-    # ---- timed region 1: device-resident (value), with per-kernel timing of the fused step kernel ----
-    sampler = ClockSampler(local)
-    sampler.start()
-    launches0 = env.launches + vn.launches
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    barrier()
-    ev[0].record()
-    for k in range(args.steps):
-        a = ring[k % 64]
-        vn._guard_reuse()
-        kev[k][0].record()
-        obs, rew, done = env.step_tensor(a)
-        kev[k][1].record()
-        # the actions of this workload do not depend on the observations: the statistics / normalisation chain of
-        # step k (two kernels + the all-reduce) runs on the side stream and overlaps env step k+1
-        vn._normalize(obs, rew, done, wait=False)
-    vn.synchronize()
-    ev[1].record()
-    barrier()
-    clocks = sampler.stop()
-    ms_total = ev[0].elapsed_time(ev[1])
-    kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
-    launches = env.launches + vn.launches - launches0
-    t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total = float(t.item())
-    value = world * n * args.steps / (ms_total * 1e-3)
-    stats = env.stats()
-
-    # ---- timed region 1b: the same steps, each one timed separately after an L2 flush (cold persistent state) ----
-    kf = min(args.steps, 50)
-    fev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(kf)]
-    barrier()
-    for k in range(kf):
-        flush.fill_(float(k))                       # 192 MB > 126 MB L2: evicts state, mocap table and model
-        fev[k][0].record()
-        vn.step_tensor(ring[k % 64])                # step kernel + statistics chain, serialised (wait=True)
-        fev[k][1].record()
-    barrier()
-    tf = torch.tensor([sum(a.elapsed_time(b) for a, b in fev)], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(tf, op=dist.ReduceOp.MAX)
-    value_flushed = world * n * kf / (float(tf.item()) * 1e-3)
-
-    # ---- timed region 2: end to end through the numpy API (host actions in, host obs/rew/done out) ----
-    e2e = None
-    if not args.no_e2e:
-        host_actions = [np.random.default_rng(rank * 1000 + k).uniform(-1, 1, (n, env.act_dim)).astype(np.float32)
-                        for k in range(8)]
-        k2 = max(10, args.steps // 4)
-        for k in range(3):
-            vn.step(host_actions[k % 8])
-        barrier()
-        flush.fill_(1.0)
-        barrier()
-        ev2 = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-        ev2[0].record()
-        acc = 0.0
-        for k in range(k2):
-            o, r, d, infos = vn.step(host_actions[k % 8])
-            acc += float(r[0])
-        ev2[1].record()
-        barrier()
-        t2 = torch.tensor([ev2[0].elapsed_time(ev2[1])], device=dev, dtype=torch.float64)
+    def max_over_ranks(ms: float) -> float:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
         if world > 1:
-            dist.all_reduce(t2, op=dist.ReduceOp.MAX)
-        e2e = {"value": world * n * k2 / (float(t2.item()) * 1e-3), "unit": "env-steps/s",
-               "h2d_bytes_per_step": n * env.act_dim * 4, "d2h_bytes_per_step": n * (2 * env.obs_dim * 4 + 4 + 1),   # obs, terminal obs, reward, done
-               "steps": k2}
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def measure(env_id, n, integrator, steps, warmup, with_clocks=False, flushed_steps=0, e2e_steps=0):
+        """one workload on this rank's GPU: W warm-up steps, then K timed steps of every flavour"""
+        cfg = EnvConfig(env_id=env_id, integrator=integrator)
+        env = B200MimicVecEnv(env_id, num_envs=n, device=f"cuda:{local}", seed=rank, cfg=cfg, env_id_offset=rank * n)
+        vn = B200VecNormalize(env, distributed=world > 1)
+        g = torch.Generator(device=dev)
+        g.manual_seed(1234 + rank)
+        ring = torch.rand(64, n, env.act_dim, device=dev, generator=g) * 2 - 1     # pre-generated action ring (§8d)
+        out = {"exchange": vn.exchange, "frame_skip": env.spec.frame_skip, "act_dim": env.act_dim,
+               "obs_dim": env.obs_dim, "lanes_per_env": env.launch_info()["lanes_per_env"]}
+        vn.reset_tensor()
+        for k in range(warmup):
+            vn.step_tensor(ring[k % 64])
+        barrier()
+        env.reset_stats()
+        # ---- device-resident, statistics chain overlapped (value) + per-kernel timing of the fused step kernel ----
+        sampler = ClockSampler(local) if with_clocks else None
+        if sampler:
+            sampler.start()
+        launches0 = env.launches + vn.launches
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        barrier()
+        ev[0].record()
+        for k in range(steps):
+            a = ring[k % 64]
+            vn._guard_reuse()
+            vn._attach_next()
+            kev[k][0].record()
+            obs, rew, done = env.step_tensor(a)
+            kev[k][1].record()
+            # the actions of this workload do not depend on the observations: the statistics exchange + normalisation
+            # kernel of step k runs on the side stream and overlaps env step k+1
+            vn._normalize(obs, rew, done, wait=False)
+        vn.synchronize()
+        ev[1].record()
+        barrier()
+        if sampler:
+            out["clocks"] = sampler.stop()
+        ms_total = max_over_ranks(ev[0].elapsed_time(ev[1]))
+        out["ms_per_step"] = ms_total / steps
+        out["value"] = world * n * steps / (ms_total * 1e-3)
+        out["kernel_ms"] = float(np.mean([a.elapsed_time(b) for a, b in kev]))
+        out["launches"] = env.launches + vn.launches - launches0
+        out["stats"] = env.stats()
+        # ---- the same steps as a policy sees them: the normalised observation of step k before step k+1 starts ----
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        barrier()
+        ev[0].record()
+        for k in range(steps):
+            vn.step_tensor(ring[k % 64])                 # wait=True: step -> exchange/merge/normalise, serialised
+        ev[1].record()
+        barrier()
+        ms_ser = max_over_ranks(ev[0].elapsed_time(ev[1]))
+        out["value_serialized"] = world * n * steps / (ms_ser * 1e-3)
+        # ---- every step timed alone after an L2 flush (cold persistent state) ----
+        if flushed_steps:
+            fev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+                   for _ in range(flushed_steps)]
+            barrier()
+            for k in range(flushed_steps):
+                flush.fill_(float(k))                    # 192 MB > 126 MB L2: evicts state, mocap table and model
+                fev[k][0].record()
+                vn.step_tensor(ring[k % 64])
+                fev[k][1].record()
+            barrier()
+            tf = max_over_ranks(sum(a.elapsed_time(b) for a, b in fev))
+            out["value_l2_flushed"] = world * n * flushed_steps / (tf * 1e-3)
+        # ---- end to end through the SB3-facing numpy API (host actions in, host obs / rew / done / infos out) ----
+        if e2e_steps:
+            host_actions = [np.random.default_rng(rank * 1000 + k).uniform(-1, 1, (n, env.act_dim)).astype(np.float32)
+                            for k in range(8)]
+            for k in range(3):
+                vn.step(host_actions[k % 8])
+            barrier()
+            flush.fill_(1.0)
+            barrier()
+            ev2 = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+            ev2[0].record()
+            acc, n_term = 0.0, 0
+            for k in range(e2e_steps):
+                o, r, d, infos = vn.step(host_actions[k % 8])
+                acc += float(r[0])
+                n_term += int(d.sum())
+            ev2[1].record()
+            barrier()
+            t2 = max_over_ranks(ev2[0].elapsed_time(ev2[1]))
+            out["e2e"] = {"value": world * n * e2e_steps / (t2 * 1e-3), "unit": "env-steps/s",
+                          "h2d_bytes_per_step": vn.h2d_bytes_per_step(), "d2h_bytes_per_step": vn.d2h_bytes_per_step(),
+                          "steps": e2e_steps,
+                          "api": "B200VecNormalize.step(host float32 actions) -> host obs, rew, done, infos (defaults)"}
+        vn.close()
+        return out
+
+    n = args.envs_per_gpu
+    head = measure(args.env_id, n, args.integrator, args.steps, args.warmup, with_clocks=True,
+                   flushed_steps=min(args.steps, 50), e2e_steps=0 if args.no_e2e else max(10, args.steps // 4))
+    # ---- the other GPU configurations of BASELINE.json, time-bounded (a few dozen steps each) ----
+    extra = {}
+    if not args.no_extra and args.env_id == ENV_ID and args.integrator == "rk4":
+        n2 = 65536 // world
+        m2 = measure(ENV_ID, n2, "rk4", 30, 5)
+        extra["configs[2]"] = {"workload": "MimicWalker3d straight walking, 65536 envs sharded over %d GPU(s) (%d per GPU)"
+                                           % (world, n2), "value": m2["value"], "value_serialized": m2["value_serialized"],
+                               "ms_per_step": m2["ms_per_step"], "kernel_ms": m2["kernel_ms"], "steps": 30, "warmup": 5}
+        m3 = measure(W165, 16384, "rk4", 20, 5)
+        extra["configs[3]"] = {"workload": "MimicWalker165cm65kg, synthetic loco3d mocap, RSI + termination, 16384 envs "
+                                           "per GPU x %d" % world, "value": m3["value"],
+                               "value_serialized": m3["value_serialized"], "ms_per_step": m3["ms_per_step"],
+                               "kernel_ms": m3["kernel_ms"], "steps": 20, "warmup": 5,
+                               "mean_ep_len": m3["stats"]["ep_len_sum"] / max(1.0, m3["stats"]["episodes"])}
 
     if rank == 0:
         peaks, which = _peaks()
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-        # W165 (informational runs): 597 B; flops scaled from W3D by evaluations (40 vs 20) x (19/14)^2
-        algo_bytes = ALGO_BYTES_PER_ENV_STEP if args.env_id == ENV_ID else 597.0
-        algo_flop = ALGO_FLOP_PER_ENV_STEP if args.env_id == ENV_ID else ALGO_FLOP_PER_ENV_STEP * 2 * (19 / 14) ** 2
+        kernel_ms, stats = head["kernel_ms"], head["stats"]
+        algo_bytes = ALGO_BYTES_PER_ENV_STEP if args.env_id == ENV_ID else 597.0      # SURVEY.md §8d
+        algo_flop = algo_flop_per_env_step(args.env_id, args.integrator, head["frame_skip"])
         achieved_gbs = algo_bytes * n / (kernel_ms * 1e-3) / 1e9
         fp32_peak = fp32_peak_tflops(local)
         achieved_tf = algo_flop * n / (kernel_ms * 1e-3) / 1e12
+        traffic, traffic_src = profiled_traffic(args.env_id, n, args.integrator)
         line = {
-            "metric": "env-steps/s incl. DeepMimic reward", "value": value, "unit": "env-steps/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
+            "metric": "env-steps/s incl. DeepMimic reward", "value": head["value"], "unit": "env-steps/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": head["ms_per_step"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic random actions U(-1,1) on the shipped straight-walking mocap, random-init (RSI) states",
             "config": {"workload": (W3D_WORKLOAD % n) if args.env_id == ENV_ID else
                                    ("MimicWalker165cm65kg on the synthetic loco3d mocap, %d envs per GPU, RSI + early "
                                     "termination (BASELINE.json configs[3])" % n),
-                       "envs_per_gpu": n, "integrator": args.integrator, "frame_skip": env.spec.frame_skip,
-                       "parallelism": f"env-sharded x{world}",
-                       "l2": "value: the persistent env state (%.1f MB) is re-read every step as in a real rollout; "
-                             "value_l2_flushed: every step re-timed alone after a 192 MB L2 flush" % (n * 720 / 1e6),
-                       "lanes_per_env": env.launch_info()["lanes_per_env"]},
-            "value_l2_flushed": value_flushed,
-            "clocks": clocks,
-            "e2e": e2e,
-            "gpu_launches": launches,
+                       "envs_per_gpu": n, "integrator": args.integrator, "frame_skip": head["frame_skip"],
+                       "parallelism": f"env-sharded x{world}", "statistics_exchange": head["exchange"],
+                       "l2": "value / value_serialized: the persistent env state (%.1f MB) is re-read every step as in "
+                             "a real rollout; value_l2_flushed: every step re-timed alone after a 192 MB L2 flush"
+                             % (n * 720 / 1e6),
+                       "lanes_per_env": head["lanes_per_env"]},
+            # value: statistics kernel of step k overlaps env step k+1 (legal for actions that do not depend on the
+            # observations); value_serialized: what a policy sees - step, exchange + merge + normalise, next step
+            "value_serialized": head["value_serialized"],
+            "value_l2_flushed": head.get("value_l2_flushed"),
+            "clocks": head.get("clocks"),
+            "e2e": head.get("e2e"),
+            "gpu_launches": head["launches"],
             "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
                          "frac": achieved_gbs / hbm_peak,
-                         # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full (profiles/r01_step_kernel_final.md)
-                         "traffic": 2836736 if (args.env_id == ENV_ID and n == 4096) else None, "peak_source": which,
+                         "traffic": traffic, "traffic_source": traffic_src, "peak_source": which,
                          "kernel": "mimic_step_kernel", "kernel_ms": kernel_ms,
                          "note": "latency/FP32-bound by construction: %d algorithmic bytes per env-step" % algo_bytes},
             "fp32": {"achieved_tflops": achieved_tf, "peak_tflops": fp32_peak,
@@ -357,6 +419,7 @@ def main():
                               "reset_rate_per_env_step": stats["episodes"] / max(1.0, stats["env_steps"]),
                               "solver_iters_per_eval": stats["solver_iters"] / max(1.0, stats["dyn_evals"]),
                               "solver_capped_frac": stats["solver_capped"] / max(1.0, stats["dyn_evals"])},
+            "extra": extra,
         }
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_single()

@@ -73,6 +73,13 @@ struct DrlEnv {
   // 1 = fd_v1.cuh) and the per-evaluation CTA barrier; A/B runs of kernel variants without rebuilding
   int fd_version = 2;
   int stage_barrier = 1;
+  // per-step statistics rows (one per thread block of the step kernel) + the ticket that elects the summing block
+  double* cta_rows = nullptr;
+  unsigned* cta_ticket = nullptr;
+  // fused VecNormalize moments (drl_attach_vecnorm): borrowed device pointers
+  float* vn_ret = nullptr;
+  float vn_gamma = 0.f;
+  double* vn_packed = nullptr;
 };
 
 static int env_int(const char* name, int dflt) {
@@ -108,7 +115,8 @@ extern "C" int drl_destroy(DrlEnv* e) {
   cudaSetDevice(e->cfg.device);
   void* ptrs[] = {e->d_model, e->state_f, e->state_i, e->state_as, e->state_d, e->extras_last, e->stats, e->ref, e->step_vel,
                   e->step_last_comx, e->des_vel_prefix, e->step_off, e->step_len, e->left_step, e->ring_len,
-                  e->ring_ret, e->ring_head, e->debug, e->speed_profile, e->ring_rsi_pos, e->ring_et_pos, e->ring_difficult};
+                  e->ring_ret, e->ring_head, e->debug, e->speed_profile, e->ring_rsi_pos, e->ring_et_pos, e->ring_difficult,
+                  e->cta_rows, e->cta_ticket};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   delete e;
@@ -131,6 +139,14 @@ static int alloc_state(DrlEnv* e, size_t N) {
   CUDA_TRY(cudaMalloc(&e->ring_et_pos, e->ring_cap * sizeof(int)));
   CUDA_TRY(cudaMalloc(&e->ring_difficult, e->ring_cap));
   CUDA_TRY(cudaMalloc(&e->ring_head, sizeof(unsigned long long)));
+  {
+    // the smallest CTA the library launches carries 32 / G environments
+    const size_t max_blocks = (N + (32 / e->G) - 1) / (32 / e->G);
+    const size_t row = 2 * (size_t)e->cfg.obs_dim + 2 + DRL_STATS_COUNT;
+    CUDA_TRY(cudaMalloc(&e->cta_rows, max_blocks * row * sizeof(double)));
+    CUDA_TRY(cudaMalloc(&e->cta_ticket, sizeof(unsigned)));
+    CUDA_TRY(cudaMemset(e->cta_ticket, 0, sizeof(unsigned)));
+  }
   CUDA_TRY(cudaMemset(e->state_f, 0, N * 4 * e->G * sizeof(float)));
   CUDA_TRY(cudaMemset(e->state_i, 0, N * kCurCount8 * sizeof(int)));
   CUDA_TRY(cudaMemset(e->state_d, 0, N * 4 * sizeof(double)));
@@ -148,7 +164,7 @@ static void free_state(DrlEnv* e) {
   void** ptrs[] = {(void**)&e->d_model, (void**)&e->state_f, (void**)&e->state_i, (void**)&e->state_as,
                    (void**)&e->state_d, (void**)&e->extras_last, (void**)&e->stats, (void**)&e->ring_len,
                    (void**)&e->ring_ret, (void**)&e->ring_head, (void**)&e->ring_rsi_pos, (void**)&e->ring_et_pos,
-                   (void**)&e->ring_difficult};
+                   (void**)&e->ring_difficult, (void**)&e->cta_rows, (void**)&e->cta_ticket};
   for (void** p : ptrs) {
     if (*p) cudaFree(*p);
     *p = nullptr;
@@ -444,6 +460,8 @@ static StepArgs make_args(DrlEnv* e) {
   a.speed_profile_len = e->speed_profile_len;
   a.playback = e->playback;
   a.stage_barrier = e->stage_barrier;
+  a.cta_rows = e->cta_rows; a.cta_ticket = e->cta_ticket;
+  a.vn_ret = e->vn_ret; a.vn_gamma = e->vn_gamma; a.packed = e->vn_packed;
   if (e->playback) a.frame_skip = 0;
   a.debug = e->debug;
   return a;
@@ -473,6 +491,14 @@ extern "C" int drl_step(DrlEnv* e, const float* actions, float* obs, float* rew,
   if (e->debug && rk4) return fail(DRL_ERR_UNSUPPORTED, "drl_step: the dump variant exists for the Euler integrator only");
   CUDA_TRY(launch_step(a, e->nv, e->G, rk4, 0, e->block, e->debug != nullptr, e->fd_version,
                        (cudaStream_t)stream));
+  return DRL_OK;
+}
+
+extern "C" int drl_attach_vecnorm(DrlEnv* e, float* ret, float gamma, double* packed) {
+  if (!e) return fail(DRL_ERR_INVALID, "drl_attach_vecnorm: null env");
+  if ((ret == nullptr) != (packed == nullptr))
+    return fail(DRL_ERR_INVALID, "drl_attach_vecnorm: pass both tensors, or two nulls to detach");
+  e->vn_ret = ret; e->vn_gamma = gamma; e->vn_packed = packed;
   return DRL_OK;
 }
 
@@ -562,6 +588,17 @@ extern "C" int drl_set_det_init_counters(DrlEnv* e, const int32_t* counts) {
   CUDA_TRY(cudaDeviceSynchronize());
   CUDA_TRY(cudaMemcpy2D(e->state_i + kCurNDet, kCurCount8 * sizeof(int), counts, sizeof(int), sizeof(int), (size_t)n,
                         cudaMemcpyHostToDevice));
+  return DRL_OK;
+}
+
+extern "C" int drl_set_seed(DrlEnv* e, uint64_t seed) {
+  if (!e) return fail(DRL_ERR_INVALID, "drl_set_seed: null env");
+  if (!e->have_model) return fail(DRL_ERR_STATE, "drl_set_seed: upload the model first");
+  e->cfg.seed = seed;
+  e->hm.seed = seed;
+  CUDA_TRY(cudaSetDevice(e->cfg.device));
+  CUDA_TRY(cudaDeviceSynchronize());          // enqueued steps may still read the model block
+  CUDA_TRY(cudaMemcpy(e->d_model, &e->hm, sizeof(DevModel), cudaMemcpyHostToDevice));
   return DRL_OK;
 }
 

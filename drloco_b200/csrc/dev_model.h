@@ -120,6 +120,13 @@ struct StepArgs {
   int playback;                      // kinematic playback: the state is set from the mocap instead of simulated
   int stage_barrier;                 // CTA barrier before every dynamics evaluation (instruction-cache sharing)
   float* debug;                      // nullable: per-env dump of one forward evaluation (tests)
+  // per-step statistics without atomics: every thread block writes one row of sums, the last block to finish adds them
+  double* cta_rows;                  // [grid][2*obs_dim + 2 + DRL_STATS_COUNT]
+  unsigned* cta_ticket;
+  // fused VecNormalize (drl_attach_vecnorm; null = not attached)
+  float* vn_ret;                     // [N] discounted-return accumulator, in/out
+  float vn_gamma;
+  double* packed;                    // [2*obs_dim + 3] batch moments of the step, out
 };
 
 }  // namespace drl

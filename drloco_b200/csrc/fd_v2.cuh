@@ -124,9 +124,14 @@ struct EnvSmem2 {
       float Ib[kMaxBody][12];   // spatial inertia about O: m, h[3], Ixx Ixy Ixz Iyy Iyz Izz
       float axw[G][4];          // joint axes in world orientation
     };
-    // staging of the per-corner contact Hessians for the per-box sums: [box][entry 0..26][corner 0..7].  Written and
-    // consumed at the start of a solver pass, when the four arrays above are dead (Fd is rewritten right after).
-    float Wred[(G == 16 ? 2 : 4) * 27 * 8];
+    // Solver-time tenants of the same storage (the body frames, body inertias and joint axes are dead by then):
+    // Wred = staging of the per-corner contact Hessians for the per-box sums, [box][entry 0..26][corner 0..7], written
+    // and consumed at the start of a solver pass (Fd is rewritten right after); sph = the touching capsule-end contacts
+    // of each lane (rare), which persist over the solver passes and therefore sit behind Wred, clear of Fd.
+    struct {
+      float Wred[(G == 16 ? 2 : 4) * 27 * 8];
+      float sph[G][12];
+    };
   };
   float Ic[kMaxBody][12];   // composite
   union {
@@ -142,6 +147,7 @@ struct EnvSmem2 {
     float Mt[kMaxBody * 56];
   };
   float obsbuf[kMaxObs];
+  int cnt[4];               // solver passes, capped evaluations of this control step (statistics)
 };
 static_assert(sizeof(EnvSmem2<16>) % 16 == 0 && sizeof(EnvSmem2<32>) % 16 == 0, "vector loads need 16-byte rows");
 
@@ -270,27 +276,125 @@ __device__ __forceinline__ void subtree_scan(const float* src, float* dst, int s
   dst[0] = root;
 }
 
+// one touching contact candidate: point (relative to O, at mid-penetration), D = 1 / R of its pyramid rows, friction,
+// reference acceleration of the four rows
+struct Contact {
+  float Px, Py, Pz, D, mu, ar[4];
+};
+__device__ __forceinline__ void st_contact(float* p, const Contact& c) {
+  *reinterpret_cast<float4*>(p) = make_float4(c.Px, c.Py, c.Pz, c.D);
+  *reinterpret_cast<float4*>(p + 4) = make_float4(c.mu, c.ar[0], c.ar[1], c.ar[2]);
+  p[8] = c.ar[3];
+}
+__device__ __forceinline__ Contact ld_contact(const float* p) {
+  const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+  return Contact{a.x, a.y, a.z, a.w, b.x, {b.y, b.z, b.w, p[8]}};
+}
+
+// contact point, regulariser and reference accelerations of candidate s on body b at signed distance dist
+template <int G, bool BOX>
+__device__ __forceinline__ void contact_setup(const DevModel& M, const EnvSmem2<G>& E, int s, int b, float dist,
+                                              Contact& c) {
+  const float4 r0 = *reinterpret_cast<const float4*>(&E.bodyR[b][0]);
+  const float4 r1 = *reinterpret_cast<const float4*>(&E.bodyR[b][4]);
+  const float4 r2 = *reinterpret_cast<const float4*>(&E.bodyR[b][8]);
+  const float x = M.cand_pos[s][0], y = M.cand_pos[s][1], z = M.cand_pos[s][2];
+  if (BOX) {
+    const float ux = M.cand_aux[s][0], uy = M.cand_aux[s][1], uz = M.cand_aux[s][2];
+    c.Px = (r0.w + r0.x * ux + r0.y * uy + r0.z * uz) + (r0.x * x + r0.y * y + r0.z * z);
+    c.Py = (r1.w + r1.x * ux + r1.y * uy + r1.z * uz) + (r1.x * x + r1.y * y + r1.z * z);
+    c.Pz = (r2.w + r2.x * ux + r2.y * uy + r2.z * uz) + (r2.x * x + r2.y * y + r2.z * z) - 0.5f * dist;
+  } else {
+    const float rad = M.cand_aux[s][0];
+    c.Px = r0.w + (r0.x * x + r0.y * y + r0.z * z);
+    c.Py = r1.w + (r1.x * x + r1.y * y + r1.z * z);
+    c.Pz = r2.w + (r2.x * x + r2.y * y + r2.z * z) - rad - 0.5f * dist;
+  }
+  const float mu = M.cand_mu[s];
+  const float imp = impedance(M, dist);
+  // D = 1 / (2 mu^2 R_n),  R_n = (1-imp)/imp * invweight * (1 + mu^2)
+  const float Rn = fmaxf(kMinVal, (1.f - imp) * M.body_invw_tran[b] * (1.f + mu * mu));
+  c.D = imp * fast_rcp(2.f * mu * mu * Rn);
+  c.mu = mu;
+  // reference acceleration of the four pyramid rows: aref = -B (J v) - K imp dist   (E.V is complete since step 4)
+  const Vec6 Vb = ld6(E.V[b]);
+  float ux, uy, uz;
+  cross3(ux, uy, uz, Vb.w0, Vb.w1, Vb.w2, c.Px, c.Py, c.Pz);
+  ux += Vb.v0; uy += Vb.v1; uz += Vb.v2;
+  const float base = -M.Kc * imp * dist;
+  c.ar[0] = -M.Bc * (uz + mu * ux) + base;
+  c.ar[1] = -M.Bc * (uz - mu * ux) + base;
+  c.ar[2] = -M.Bc * (uz + mu * uy) + base;
+  c.ar[3] = -M.Bc * (uz - mu * uy) + base;
+}
+
+// wrench-space Hessian of the active pyramid rows `bt` of a contact: w = (P x d, d), W = sum D w w^T (wv[0..20], packed
+// upper triangle) and rhs wrench U = sum D aref w (wv[21..26]); zeros when no row is active
+__device__ __forceinline__ void contact_hessian(const Contact& c, unsigned bt, float (&wv)[28]) {
+#pragma unroll
+  for (int i = 0; i < 28; i++) wv[i] = 0.f;
+  if (bt) {
+    const float D = c.D, mu = c.mu;
+    const float s0 = (bt & 1u) ? 1.f : 0.f, s1 = (bt & 2u) ? 1.f : 0.f;
+    const float s2 = (bt & 4u) ? 1.f : 0.f, s3 = (bt & 8u) ? 1.f : 0.f;
+    const float Qxx = D * mu * mu * (s0 + s1), Qyy = D * mu * mu * (s2 + s3), Qzz = D * (s0 + s1 + s2 + s3);
+    const float Qxz = D * mu * (s0 - s1), Qyz = D * mu * (s2 - s3);
+    const float Px = c.Px, Py = c.Py, Pz = c.Pz;
+    // X = [P]x Q with Q rows (Qxx,0,Qxz) (0,Qyy,Qyz) (Qxz,Qyz,Qzz);  Nn row i = P x X_i
+    const float X00 = Py * Qxz, X01 = -Pz * Qyy + Py * Qyz, X02 = -Pz * Qyz + Py * Qzz;
+    const float X10 = Pz * Qxx - Px * Qxz, X11 = -Px * Qyz, X12 = Pz * Qxz - Px * Qzz;
+    const float X20 = -Py * Qxx, X21 = Px * Qyy, X22 = -Py * Qxz + Px * Qyz;
+    float t0, t1, t2;
+    cross3(wv[sym6(0, 0)], wv[sym6(0, 1)], wv[sym6(0, 2)], Px, Py, Pz, X00, X01, X02);
+    cross3(t0, wv[sym6(1, 1)], wv[sym6(1, 2)], Px, Py, Pz, X10, X11, X12);
+    cross3(t1, t2, wv[sym6(2, 2)], Px, Py, Pz, X20, X21, X22);
+    (void)t0; (void)t1; (void)t2;
+    wv[sym6(0, 3)] = X00; wv[sym6(0, 4)] = X01; wv[sym6(0, 5)] = X02;
+    wv[sym6(1, 3)] = X10; wv[sym6(1, 4)] = X11; wv[sym6(1, 5)] = X12;
+    wv[sym6(2, 3)] = X20; wv[sym6(2, 4)] = X21; wv[sym6(2, 5)] = X22;
+    wv[sym6(3, 3)] = Qxx; wv[sym6(3, 5)] = Qxz; wv[sym6(4, 4)] = Qyy; wv[sym6(4, 5)] = Qyz;
+    wv[sym6(5, 5)] = Qzz;
+    const float a0 = s0 * c.ar[0], a1 = s1 * c.ar[1], a2 = s2 * c.ar[2], a3 = s3 * c.ar[3];
+    const float gx = D * mu * (a0 - a1), gy = D * mu * (a2 - a3), gz = D * (a0 + a1 + a2 + a3);
+    cross3(wv[21], wv[22], wv[23], Px, Py, Pz, gx, gy, gz);
+    wv[24] = gx; wv[25] = gy; wv[26] = gz;
+  }
+}
+
+// which pyramid rows of a contact pull (J_i a - aref_i < 0) at the body twist Tb = S_b qacc
+__device__ __forceinline__ unsigned contact_rows(const Contact& c, const Vec6& Tb) {
+  float ux, uy, uz;
+  cross3(ux, uy, uz, Tb.w0, Tb.w1, Tb.w2, c.Px, c.Py, c.Pz);
+  ux += Tb.v0; uy += Tb.v1; uz += Tb.v2;
+  const float mu = c.mu;
+  return ((uz + mu * ux - c.ar[0] < 0.f) ? 1u : 0u) | ((uz - mu * ux - c.ar[1] < 0.f) ? 2u : 0u) |
+         ((uz + mu * uy - c.ar[2] < 0.f) ? 4u : 0u) | ((uz - mu * uy - c.ar[3] < 0.f) ? 8u : 0u);
+}
+
 // Column l of the joint-space matrix H[r][c] = S_c . (Ic*_{body(r)} S_r) for r = c or a descendant of c (CRBA on the
 // contact-augmented composite inertias; E.Fd holds Ic* S).  Each lane computes its column at and below the diagonal; the
 // part above comes from the transposed entries through shared memory.  E.Mt aliases V/Ab/T/W/U: callers guarantee
 // those are dead.  Output in registers H[0..NV-1] (armature on the diagonal).
 template <int NV, int G>
-__device__ __forceinline__ void mass_column2(EnvSmem2<G>& E, const LaneConst& L, const Vec6& S, float (&H)[NV + 1]) {
+__device__ __forceinline__ void mass_column2(const DevModel& M, EnvSmem2<G>& E, const LaneConst& L, const Vec6& S,
+                                             float (&H)[NV + 1]) {
   constexpr int kMs = (NV % 2 == 0) ? NV + 1 : NV + 2;
   static_assert(NV * kMs <= (int)(sizeof(E.Mt) / sizeof(float)), "Mt too small");
   const int l = L.l;
-  const unsigned lowmask = L.isdof ? (L.desc | (1u << l)) : 0u;
+  const unsigned me = L.isdof ? (1u << l) : 0u;
 #pragma unroll
   for (int r = 0; r < NV; r++) {
     const float d = dot6(S, ld6(E.Fd[r]));
-    H[r] = ((lowmask >> r) & 1u) ? d : 0.f;
+    // rows at and below the diagonal: r == l or r a descendant of l
+    H[r] = (((dof_anc_mask<NV>(r) | (1u << r)) & me) != 0u) ? d : 0.f;
     if (L.isdof) E.Mt[r * kMs + l] = H[r];
   }
   __syncwarp();
+  const float arm = L.isdof ? M.dof_armature[l] : 0.f;
 #pragma unroll
   for (int r = 0; r < NV; r++) {
     if (L.isdof && r < l) H[r] = E.Mt[l * kMs + r];
-    if (r == l) H[r] += L.armature;
+    if (r == l) H[r] += arm;
   }
 }
 
@@ -300,14 +404,15 @@ __device__ __forceinline__ void mass_column2(EnvSmem2<G>& E, const LaneConst& L,
 template <int NV, int G, bool DBG>
 __device__ __forceinline__ void forward_dynamics2(const DevModel& M, EnvSmem2<G>& E, const LaneConst& L,
                                                   const ChainLane& C, float q, float v, float tau, float& a,
-                                                  ActiveSet& AS, Counters& cnt, Vec6& S, float* dbg) {
+                                                  ActiveSet& AS, Vec6& S, float* dbg) {
   using T = Topo<NV>;
   const int l = L.l;
   const bool iscomp = l < 6 * T::NCHAIN;
   // ---- 1. joint trig + velocity ------------------------------------------------------------------------------------
   {
-    float s = q - L.ref, c = 1.f;
-    if (L.isdof && L.type == 1) sincos_joint(L.sign * (q - L.ref), s, c);
+    const float ref = M.dof_ref[L.isdof ? l : 0];
+    float s = q - ref, c = 1.f;
+    if (L.isdof && L.type == 1) sincos_joint(M.dof_sign[l] * (q - ref), s, c);
     if (L.isdof) { *reinterpret_cast<float2*>(&E.cssn[l][0]) = make_float2(c, s); E.v[l] = v; }
   }
   __syncwarp();
@@ -391,88 +496,53 @@ __device__ __forceinline__ void forward_dynamics2(const DevModel& M, EnvSmem2<G>
     f.v0 += tx; f.v1 += ty; f.v2 += tz;
     st6(E.Ab[l], f);
   }
-  // contacts: candidate s = pass * G + l.  Signed distance first; the rest only for touching candidates.
-  bool cact[kNPass];
-  float cPx[kNPass], cPy[kNPass], cPz[kNPass], cD[kNPass], cmu[kNPass], car[kNPass][4];
-  int cbody[kNPass];
-  float cdist[kNPass];
+  // contacts: candidate s = pass * G + l.  Pass 0 holds the box corners (feet: the common case, kept in registers),
+  // pass 1 the capsule end spheres (a fallen walker: rare; their data lives in shared memory and every step that
+  // touches it sits in a cold branch).  Signed distance first; the rest only for touching candidates.
   const int wl = threadIdx.x & 31;
-#pragma unroll
-  for (int ps = 0; ps < kNPass; ps++) {
-    const int s = ps * G + l;
-    const bool valid = s < M.ncand;
-    const int b = valid ? M.cand_body[s] : 0;
-    cbody[ps] = b;
-    bool act = false;
-    float dist = 0.f;
-    if (valid) {
-      const float4 r2 = *reinterpret_cast<const float4*>(&E.bodyR[b][8]);
-      const float rz = r2.x * M.cand_pos[s][0] + r2.y * M.cand_pos[s][1] + r2.z * M.cand_pos[s][2];
-      if (s < M.nbox_cand) {
-        const float cz = zO + r2.w + r2.x * M.cand_aux[s][0] + r2.y * M.cand_aux[s][1] + r2.z * M.cand_aux[s][2];
-        dist = cz + rz;
-        act = !(dist > 0.f || rz > 0.f);
-      } else {
-        dist = zO + r2.w + rz - M.cand_aux[s][0];
-        act = !(dist > 0.f);
-      }
+  bool act0 = false, act1 = false;
+  float dist0 = 0.f, dist1 = 0.f;
+  const int body0 = M.cand_body[l < M.ncand ? l : 0];
+  {
+    if (l < M.nbox_cand) {
+      const float4 r2 = *reinterpret_cast<const float4*>(&E.bodyR[body0][8]);
+      const float rz = r2.x * M.cand_pos[l][0] + r2.y * M.cand_pos[l][1] + r2.z * M.cand_pos[l][2];
+      const float cz = zO + r2.w + r2.x * M.cand_aux[l][0] + r2.y * M.cand_aux[l][1] + r2.z * M.cand_aux[l][2];
+      dist0 = cz + rz;
+      act0 = !(dist0 > 0.f || rz > 0.f);
     }
     // plane-box keeps at most the first four penetrating corners (MuJoCo mjc_PlaneBox)
-    if (ps == 0) {
-      const unsigned bal = __ballot_sync(kFull, act && s < M.nbox_cand);
-      const unsigned seg = 0xFFu << (wl & ~7);
-      const int rank = __popc(bal & seg & ((1u << wl) - 1u));
-      if (s < M.nbox_cand && rank >= 4) act = false;
+    const unsigned bal = __ballot_sync(kFull, act0);
+    const unsigned seg = 0xFFu << (wl & ~7);
+    const int rank = __popc(bal & seg & ((1u << wl) - 1u));
+    if (rank >= 4) act0 = false;
+    const int s1 = G + l;
+    if (s1 < M.ncand) {
+      const int b1 = M.cand_body[s1];
+      const float4 r2 = *reinterpret_cast<const float4*>(&E.bodyR[b1][8]);
+      const float rz = r2.x * M.cand_pos[s1][0] + r2.y * M.cand_pos[s1][1] + r2.z * M.cand_pos[s1][2];
+      dist1 = zO + r2.w + rz - M.cand_aux[s1][0];
+      act1 = !(dist1 > 0.f);
     }
-    cact[ps] = act; cdist[ps] = dist;
-    cPx[ps] = cPy[ps] = cPz[ps] = 0.f; cD[ps] = 0.f; cmu[ps] = 0.f;
-    car[ps][0] = car[ps][1] = car[ps][2] = car[ps][3] = 0.f;
   }
   __syncwarp();   // E.Ab (body forces) complete
-  const bool any0 = __any_sync(kFull, cact[0]);
-  const bool sph_any = __builtin_expect(__any_sync(kFull, cact[1]), 0);   // capsule contacts: fallen walkers only
+  const bool any0 = __any_sync(kFull, act0);
+  const bool sph_any = __builtin_expect(__any_sync(kFull, act1), 0);
   unsigned conmask = 0;
-#pragma unroll
-  for (int ps = 0; ps < kNPass; ps++) {
-    if (!(ps == 0 ? any0 : sph_any)) continue;
-    if (cact[ps]) {
-      const int s = ps * G + l, b = cbody[ps];
-      const float dist = cdist[ps];
-      const float4 r0 = *reinterpret_cast<const float4*>(&E.bodyR[b][0]);
-      const float4 r1 = *reinterpret_cast<const float4*>(&E.bodyR[b][4]);
-      const float4 r2 = *reinterpret_cast<const float4*>(&E.bodyR[b][8]);
-      float x = M.cand_pos[s][0], y = M.cand_pos[s][1], z = M.cand_pos[s][2];
-      float Px, Py, Pz;
-      if (s < M.nbox_cand) {
-        const float ux = M.cand_aux[s][0], uy = M.cand_aux[s][1], uz = M.cand_aux[s][2];
-        Px = (r0.w + r0.x * ux + r0.y * uy + r0.z * uz) + (r0.x * x + r0.y * y + r0.z * z);
-        Py = (r1.w + r1.x * ux + r1.y * uy + r1.z * uz) + (r1.x * x + r1.y * y + r1.z * z);
-        Pz = (r2.w + r2.x * ux + r2.y * uy + r2.z * uz) + (r2.x * x + r2.y * y + r2.z * z) - 0.5f * dist;
-      } else {
-        const float rad = M.cand_aux[s][0];
-        Px = r0.w + (r0.x * x + r0.y * y + r0.z * z);
-        Py = r1.w + (r1.x * x + r1.y * y + r1.z * z);
-        Pz = r2.w + (r2.x * x + r2.y * y + r2.z * z) - rad - 0.5f * dist;
-      }
-      cPx[ps] = Px; cPy[ps] = Py; cPz[ps] = Pz;
-      const float mu = M.cand_mu[s];
-      const float imp = impedance(M, dist);
-      // D = 1 / (2 mu^2 R_n),  R_n = (1-imp)/imp * invweight * (1 + mu^2)
-      const float Rn = fmaxf(kMinVal, (1.f - imp) * M.body_invw_tran[b] * (1.f + mu * mu));
-      cD[ps] = imp * fast_rcp(2.f * mu * mu * Rn);
-      cmu[ps] = mu;
-      conmask |= 1u << b;
-      // reference acceleration of the four pyramid rows: aref = -B (J v) - K imp dist
-      const Vec6 Vb = ld6(E.V[b]);
-      float ux, uy, uz;
-      cross3(ux, uy, uz, Vb.w0, Vb.w1, Vb.w2, Px, Py, Pz);
-      ux += Vb.v0; uy += Vb.v1; uz += Vb.v2;
-      const float base = -M.Kc * imp * dist;
-      car[ps][0] = -M.Bc * (uz + mu * ux) + base;
-      car[ps][1] = -M.Bc * (uz - mu * ux) + base;
-      car[ps][2] = -M.Bc * (uz + mu * uy) + base;
-      car[ps][3] = -M.Bc * (uz - mu * uy) + base;
+  Contact c0 = {0.f, 0.f, 0.f, 0.f, 0.f, {0.f, 0.f, 0.f, 0.f}};
+  if (any0 && act0) {
+    contact_setup<G, true>(M, E, l, body0, dist0, c0);
+    conmask |= 1u << body0;
+  }
+  if (sph_any) {
+    Contact c1 = {0.f, 0.f, 0.f, 0.f, 0.f, {0.f, 0.f, 0.f, 0.f}};
+    const int b1 = M.cand_body[G + l < M.ncand ? G + l : 0];
+    if (act1) {
+      contact_setup<G, false>(M, E, G + l, b1, dist1, c1);
+      conmask |= 1u << b1;
     }
+    __syncwarp();          // E.sph shares storage with the body frames read above
+    if (act1) st_contact(E.sph[l], c1);
   }
   // bodies with a contact in either environment of the warp (W/U are kept valid for the union in both)
   conmask = __reduce_or_sync(kFull, conmask);
@@ -482,31 +552,30 @@ __device__ __forceinline__ void forward_dynamics2(const DevModel& M, EnvSmem2<G>
   float rhs0 = 0.f;
   if (L.isdof) {
     const float cb = dot6(S, ld6(E.Ab[L.body]));
-    rhs0 = tau - L.damping * v - cb;
+    rhs0 = tau - M.dof_damping[l] * v - cb;
     if (DBG) { dbg[0 * 32 + l] = cb; dbg[1 * 32 + l] = rhs0; }
   }
   // ---- joint limits ----------------------------------------------------------------------------------------------------------
   float lsg = 0.f, lD = 0.f, laref = 0.f;
-  if (L.isdof && L.limited) {
+  if (L.isdof && M.dof_limited[l]) {
     float dist = 0.f;
-    if (q < L.lo) { lsg = 1.f; dist = q - L.lo; }
-    else if (q > L.hi) { lsg = -1.f; dist = L.hi - q; }
+    const float lo = M.dof_lo[l], hi = M.dof_hi[l];
+    if (q < lo) { lsg = 1.f; dist = q - lo; }
+    else if (q > hi) { lsg = -1.f; dist = hi - q; }
     if (lsg != 0.f) {
       const float imp = impedance(M, dist);
-      lD = imp * fast_rcp(fmaxf(kMinVal, (1.f - imp) * L.invw));
+      lD = imp * fast_rcp(fmaxf(kMinVal, (1.f - imp) * M.dof_invw[l]));
       laref = -M.Bc * lsg * v - M.Kc * imp * dist;
     }
   }
-  cnt.evals++;
   // ---- 8. active-set iteration -----------------------------------------------------------------------------------------------
   // The active set of the previous evaluation (same lane <-> same contact candidate) is the starting guess; a contact
   // or limit that was not present before starts with all of its rows active.  Without any constraint in the warp the
   // loop body runs once and is the plain solve M qacc = rhs0.
-#pragma unroll
-  for (int ps = 0; ps < kNPass; ps++) {
-    if (!cact[ps]) AS.bits[ps] = 0u;
-    else if (!((AS.prev_act >> ps) & 1u)) AS.bits[ps] = 0xFu;
-  }
+  if (!act0) AS.bits[0] = 0u;
+  else if (!(AS.prev_act & 1u)) AS.bits[0] = 0xFu;
+  if (!act1) AS.bits[1] = 0u;
+  else if (!(AS.prev_act & 2u)) AS.bits[1] = 0xFu;
   if (lsg == 0.f) AS.lbit = false;
   else if (!AS.prev_lim) AS.lbit = true;
   const bool any_limit = __any_sync(kFull, lsg != 0.f);
@@ -516,9 +585,11 @@ __device__ __forceinline__ void forward_dynamics2(const DevModel& M, EnvSmem2<G>
 #pragma unroll
   for (int b = 0; b < T::NB; b++)
     if (M.body_sub[b] & conmask) subcon |= 1u << b;
+  int n_iter = 0;
+  bool capped = false;
   float H[NV + 1];
   for (int it = 0; it < kMaxSolverIter; it++) {
-    if (constrained) cnt.iters++;
+    if (constrained) n_iter++;
     if (conmask != 0u) {
       // Per-body accumulators W (21) / U (6).  Box bodies are written by their 8-lane segment (zeros when the segment
       // has no active corner), capsule-only bodies are zeroed here and filled below; no atomics anywhere, so the
@@ -530,78 +601,52 @@ __device__ __forceinline__ void forward_dynamics2(const DevModel& M, EnvSmem2<G>
           if (l < 8) E.U[b][l] = 0.f;
         }
       }
-#pragma unroll
-      for (int ps = 0; ps < kNPass; ps++) {
-        if (ps == 1 && !sph_any) continue;
-        // wrench-space Hessian of this contact's active pyramid rows: w = (P x d, d), W += D w w^T, U += D aref w
+      {
+        // box corners: the 8 lanes of a segment belong to one box = one body.  Every corner lane stages the 27 numbers
+        // of its contact (wrench-space Hessian of the active pyramid rows + rhs wrench), then the lanes share out the
+        // 27 x (number of boxes) sums over the 8 corners (fixed order: deterministic) and store the body's accumulators.
         float wv[28];
+        contact_hessian(c0, act0 ? AS.bits[0] : 0u, wv);
+        if (l < M.nbox_cand) {
+          float* dst = &E.Wred[((l >> 3) * 27) * 8 + (l & 7)];
 #pragma unroll
-        for (int i = 0; i < 28; i++) wv[i] = 0.f;
-        const unsigned bt = cact[ps] ? AS.bits[ps] : 0u;
-        if (bt) {
-          const float D = cD[ps], mu = cmu[ps];
-          const float s0 = (bt & 1u) ? 1.f : 0.f, s1 = (bt & 2u) ? 1.f : 0.f;
-          const float s2 = (bt & 4u) ? 1.f : 0.f, s3 = (bt & 8u) ? 1.f : 0.f;
-          const float Qxx = D * mu * mu * (s0 + s1), Qyy = D * mu * mu * (s2 + s3), Qzz = D * (s0 + s1 + s2 + s3);
-          const float Qxz = D * mu * (s0 - s1), Qyz = D * mu * (s2 - s3);
-          const float Px = cPx[ps], Py = cPy[ps], Pz = cPz[ps];
-          // X = [P]x Q with Q rows (Qxx,0,Qxz) (0,Qyy,Qyz) (Qxz,Qyz,Qzz);  Nn row i = P x X_i
-          const float X00 = Py * Qxz, X01 = -Pz * Qyy + Py * Qyz, X02 = -Pz * Qyz + Py * Qzz;
-          const float X10 = Pz * Qxx - Px * Qxz, X11 = -Px * Qyz, X12 = Pz * Qxz - Px * Qzz;
-          const float X20 = -Py * Qxx, X21 = Px * Qyy, X22 = -Py * Qxz + Px * Qyz;
-          float t0, t1, t2;
-          cross3(wv[sym6(0, 0)], wv[sym6(0, 1)], wv[sym6(0, 2)], Px, Py, Pz, X00, X01, X02);
-          cross3(t0, wv[sym6(1, 1)], wv[sym6(1, 2)], Px, Py, Pz, X10, X11, X12);
-          cross3(t1, t2, wv[sym6(2, 2)], Px, Py, Pz, X20, X21, X22);
-          (void)t0; (void)t1; (void)t2;
-          wv[sym6(0, 3)] = X00; wv[sym6(0, 4)] = X01; wv[sym6(0, 5)] = X02;
-          wv[sym6(1, 3)] = X10; wv[sym6(1, 4)] = X11; wv[sym6(1, 5)] = X12;
-          wv[sym6(2, 3)] = X20; wv[sym6(2, 4)] = X21; wv[sym6(2, 5)] = X22;
-          wv[sym6(3, 3)] = Qxx; wv[sym6(3, 5)] = Qxz; wv[sym6(4, 4)] = Qyy; wv[sym6(4, 5)] = Qyz;
-          wv[sym6(5, 5)] = Qzz;
-          const float a0 = s0 * car[ps][0], a1 = s1 * car[ps][1], a2 = s2 * car[ps][2], a3 = s3 * car[ps][3];
-          const float gx = D * mu * (a0 - a1), gy = D * mu * (a2 - a3), gz = D * (a0 + a1 + a2 + a3);
-          cross3(wv[21], wv[22], wv[23], Px, Py, Pz, gx, gy, gz);
-          wv[24] = gx; wv[25] = gy; wv[26] = gz;
+          for (int i = 0; i < 27; i++) dst[i * 8] = wv[i];
         }
-        if (ps == 0) {
-          // pass 0 holds the box corners: the 8 lanes of a segment belong to one box = one body.  Every corner lane
-          // stages its 27 numbers, then the lanes share out the 27 x (number of boxes) sums over the 8 corners
-          // (fixed order: deterministic) and store their body's accumulators.
-          if (l < M.nbox_cand) {
-            float* dst = &E.Wred[((l >> 3) * 27) * 8 + (l & 7)];
+        __syncwarp();
 #pragma unroll
-            for (int i = 0; i < 27; i++) dst[i * 8] = wv[i];
-          }
-          __syncwarp();
+        for (int bx = 0; bx < T::NBOX; bx++) {
 #pragma unroll
-          for (int bx = 0; bx < T::NBOX; bx++) {
-#pragma unroll
-            for (int i0 = 0; i0 < 27; i0 += G) {
-              const int i = i0 + l;
-              if (i < 27 && bx * 8 < M.nbox_cand) {
-                const float4 x0 = *reinterpret_cast<const float4*>(&E.Wred[(bx * 27 + i) * 8]);
-                const float4 x1 = *reinterpret_cast<const float4*>(&E.Wred[(bx * 27 + i) * 8 + 4]);
-                const float sum = ((x0.x + x0.y) + (x0.z + x0.w)) + ((x1.x + x1.y) + (x1.z + x1.w));
-                const int b = M.cand_body[bx * 8];
-                if (i < 21) E.W[b][i] = sum; else E.U[b][i - 21] = sum;
-              }
+          for (int i0 = 0; i0 < 27; i0 += G) {
+            const int i = i0 + l;
+            if (i < 27 && bx * 8 < M.nbox_cand) {
+              const float4 x0 = *reinterpret_cast<const float4*>(&E.Wred[(bx * 27 + i) * 8]);
+              const float4 x1 = *reinterpret_cast<const float4*>(&E.Wred[(bx * 27 + i) * 8 + 4]);
+              const float sum = ((x0.x + x0.y) + (x0.z + x0.w)) + ((x1.x + x1.y) + (x1.z + x1.w));
+              const int b = M.cand_body[bx * 8];
+              if (i < 21) E.W[b][i] = sum; else E.U[b][i - 21] = sum;
             }
           }
-        } else {
-          // capsule end spheres: rare; added one contact at a time in lane order (deterministic)
-          __syncwarp();
-          for (unsigned sm = __ballot_sync(kFull, bt != 0u); sm; sm &= sm - 1) {
-            if (wl == __ffs(sm) - 1) {
-              float* Wb = E.W[cbody[ps]];
-              float* Ub = E.U[cbody[ps]];
+        }
+      }
+      if (sph_any) {
+        // capsule end spheres: added one contact at a time in lane order (deterministic)
+        float wv[28];
+        Contact c1 = {0.f, 0.f, 0.f, 0.f, 0.f, {0.f, 0.f, 0.f, 0.f}};
+        const unsigned bt = act1 ? AS.bits[1] : 0u;
+        if (bt) c1 = ld_contact(E.sph[l]);
+        contact_hessian(c1, bt, wv);
+        const int b1 = M.cand_body[G + l < M.ncand ? G + l : 0];
+        __syncwarp();
+        for (unsigned sm = __ballot_sync(kFull, bt != 0u); sm; sm &= sm - 1) {
+          if (wl == __ffs(sm) - 1) {
+            float* Wb = E.W[b1];
+            float* Ub = E.U[b1];
 #pragma unroll
-              for (int i = 0; i < 21; i++) Wb[i] += wv[i];
+            for (int i = 0; i < 21; i++) Wb[i] += wv[i];
 #pragma unroll
-              for (int i = 0; i < 6; i++) Ub[i] += wv[21 + i];
-            }
-            __syncwarp();
+            for (int i = 0; i < 6; i++) Ub[i] += wv[21 + i];
           }
+          __syncwarp();
         }
       }
       __syncwarp();
@@ -639,7 +684,7 @@ __device__ __forceinline__ void forward_dynamics2(const DevModel& M, EnvSmem2<G>
       st6(E.Fd[l], F);
     }
     __syncwarp();      // also: every lane is done with W / U before Mt (same storage) is written
-    mass_column2<NV, G>(E, L, S, H);
+    mass_column2<NV, G>(M, E, L, S, H);
     if (AS.lbit) {
 #pragma unroll
       for (int r = 0; r < NV; r++)
@@ -657,18 +702,17 @@ __device__ __forceinline__ void forward_dynamics2(const DevModel& M, EnvSmem2<G>
       __syncwarp();
     }
     bool changed = false;
-#pragma unroll
-    for (int ps = 0; ps < kNPass; ps++) {
-      if (cact[ps]) {
-        const Vec6 Tb = ld6(E.T[cbody[ps]]);
-        float ux, uy, uz;
-        cross3(ux, uy, uz, Tb.w0, Tb.w1, Tb.w2, cPx[ps], cPy[ps], cPz[ps]);
-        ux += Tb.v0; uy += Tb.v1; uz += Tb.v2;
-        const float mu = cmu[ps];
-        const unsigned nb = ((uz + mu * ux - car[ps][0] < 0.f) ? 1u : 0u) | ((uz - mu * ux - car[ps][1] < 0.f) ? 2u : 0u) |
-                            ((uz + mu * uy - car[ps][2] < 0.f) ? 4u : 0u) | ((uz - mu * uy - car[ps][3] < 0.f) ? 8u : 0u);
-        changed = changed || (nb != AS.bits[ps]);
-        AS.bits[ps] = nb;
+    if (act0) {
+      const unsigned nb = contact_rows(c0, ld6(E.T[body0]));
+      changed = nb != AS.bits[0];
+      AS.bits[0] = nb;
+    }
+    if (sph_any) {
+      if (act1) {
+        const Contact c1 = ld_contact(E.sph[l]);
+        const unsigned nb = contact_rows(c1, ld6(E.T[M.cand_body[G + l]]));
+        changed = changed || (nb != AS.bits[1]);
+        AS.bits[1] = nb;
       }
     }
     {
@@ -677,33 +721,32 @@ __device__ __forceinline__ void forward_dynamics2(const DevModel& M, EnvSmem2<G>
       AS.lbit = nl;
     }
     if (!__any_sync(kFull, changed)) break;
-    if (it == kMaxSolverIter - 1 && env_any(changed, L.emask)) cnt.capped++;
+    if (it == kMaxSolverIter - 1 && env_any(changed, L.emask)) capped = true;
     __syncwarp();      // T (same storage as W / U / Mt) is read before the next pass rewrites W
   }
-  AS.prev_act = (cact[0] ? 1u : 0u) | (cact[1] ? 2u : 0u);
+  AS.prev_act = (act0 ? 1u : 0u) | (act1 ? 2u : 0u);
   AS.prev_lim = lsg != 0.f;
+  // solver statistics (DRL_STAT_SOLVER_ITERS / _CAPPED) are kept per environment in shared memory, off the registers
+  if (l == 0) { E.cnt[0] += n_iter; E.cnt[1] += capped ? 1 : 0; }
   if (DBG) {
     dbg[(2 + NV) * 32 + l] = a;
     if (l == 0) {
       dbg[(3 + NV) * 32 + 0] = zO;
       dbg[(3 + NV) * 32 + 1] = (float)__popc(conmask);
     }
-    int nc = 0;
-#pragma unroll
-    for (int ps = 0; ps < kNPass; ps++) nc += cact[ps] ? 1 : 0;
-    dbg[(4 + NV) * 32 + l] = (float)nc;
+    dbg[(4 + NV) * 32 + l] = (float)((act0 ? 1 : 0) + (act1 ? 1 : 0));
   }
 }
 
 // Column l of the plain joint-space inertia matrix (no contact terms) from the motion vectors and composite inertias
 // left behind by forward_dynamics2: the implicit-damping solve of the Euler integrator and the test dump use it.
 template <int NV, int G>
-__device__ __forceinline__ void pure_mass_column2(EnvSmem2<G>& E, const LaneConst& L, const Vec6& S,
-                                                  float (&H)[NV + 1]) {
+__device__ __forceinline__ void pure_mass_column2(const DevModel& M, EnvSmem2<G>& E, const LaneConst& L,
+                                                  const Vec6& S, float (&H)[NV + 1]) {
   __syncwarp();
   if (L.isdof) st6(E.Fd[L.l], inertia_mul(E.Ic[L.body], S));
   __syncwarp();
-  mass_column2<NV, G>(E, L, S, H);
+  mass_column2<NV, G>(M, E, L, S, H);
   __syncwarp();
 }
 

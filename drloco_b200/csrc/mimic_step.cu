@@ -155,18 +155,26 @@ __device__ __forceinline__ void build_obs(const DevModel& M, const StepArgs& A, 
   __syncwarp();
 }
 
-// obs (optionally mirrored, mimic_env.py:440-480) from E.obsbuf to global memory; `enable` predicates the stores
+// obs (optionally mirrored, mimic_env.py:440-480) from E.obsbuf to global memory; `enable` predicates the stores.
+// ov (nullable): this lane's two entries (columns l and l + G) of the observation the step returns, kept for the fused
+// VecNormalize moments.
 template <int G, class ES>
 __device__ __forceinline__ void write_obs(const DevModel& M, ES& E, int l, bool mirror, bool enable,
-                                          float* __restrict__ dst) {
-  if (enable)
-    for (int k = l; k < M.obs_dim; k += G)
-      dst[k] = mirror ? M.mirror_obs_sign[k] * E.obsbuf[M.mirror_obs_idx[k]] : E.obsbuf[k];
+                                          float* __restrict__ dst, float* ov = nullptr) {
+  if (enable) {
+#pragma unroll
+    for (int t = 0; t < 2; t++) {
+      const int k = l + t * G;
+      if (k < M.obs_dim) {
+        const float x = mirror ? M.mirror_obs_sign[k] * E.obsbuf[M.mirror_obs_idx[k]] : E.obsbuf[k];
+        dst[k] = x;
+        if (ov) ov[t] = x;
+      }
+    }
+  }
   __syncwarp();
 }
 
-// MimicEnv.reset_model (mimic_env.py:526-572): RSI, ground-contact shift, refs.next().  Warp-uniform: every lane
-// computes a reset, the caller commits it only for environments that need one.
 // kinematics + foot-site height for either shared-memory layout
 template <int NV, int G>
 __device__ __forceinline__ void reset_kinematics(const DevModel& M, EnvSmem<G>& E, const ChainLane&, int l) {
@@ -289,6 +297,9 @@ __global__ void __launch_bounds__(128, 4) mimic_step_kernel(const StepArgs A, co
   c.rsi_step = si[kCurRsiStep]; c.n_det = si[kCurNDet]; c.resets = si[kCurResets]; c.flags = si[kCurFlags];
   float dist = sf[3 * G + kMiscDist], zoff = sf[3 * G + kMiscZoff];
   Counters cnt = {0, 0, 0};
+  if constexpr (FDV == 2) {
+    if (l == 0) { E.cnt[0] = 0; E.cnt[1] = 0; }
+  }
   // active set of the last evaluation of the previous step (bits 0-3 / 4-7: pyramid rows of the two candidates,
   // 8-9: candidates in contact, 10: limit row active, 11: limit violated)
   int* sa = A.state_as + (size_t)env * G;
@@ -359,7 +370,7 @@ __global__ void __launch_bounds__(128, 4) mimic_step_kernel(const StepArgs A, co
       const bool blown = env_any(L.isdof && (!(fabsf(q) <= 1e10f) || !(fabsf(v) <= 1e10f)), L.emask);
       bad = bad || blown;
     }
-    if (bad) { q = L.ref; v = 0.f; a = 0.f; }      // park the environment on a harmless state; it resets below
+    if (bad) { q = M.dof_ref[jd]; v = 0.f; a = 0.f; }   // park the environment on a harmless state; it resets below
     if (RK4) {
       const float q0 = q, v0 = v;
       float accq = 0.f, accv = 0.f;
@@ -371,7 +382,7 @@ __global__ void __launch_bounds__(128, 4) mimic_step_kernel(const StepArgs A, co
         if (A.stage_barrier) __syncthreads();
         if constexpr (FDV == 2) {
           Vec6 Sj;
-          forward_dynamics2<NV, G, DBG>(M, E, L, CL, q, v, tau, a, AS, cnt, Sj, dbgp);
+          forward_dynamics2<NV, G, DBG>(M, E, L, CL, q, v, tau, a, AS, Sj, dbgp);
         } else {
           forward_dynamics<NV, G, DBG>(M, E, L, q, v, tau, a, AS, cnt, dbgp);
         }
@@ -393,8 +404,8 @@ __global__ void __launch_bounds__(128, 4) mimic_step_kernel(const StepArgs A, co
       float Ma = 0.f;
       if constexpr (FDV == 2) {
         Vec6 Sj;
-        forward_dynamics2<NV, G, DBG>(M, E, L, CL, q, v, tau, a, AS, cnt, Sj, dbgp);
-        pure_mass_column2<NV, G>(E, L, Sj, Hc);     // E.acc holds the constrained qacc of every dof
+        forward_dynamics2<NV, G, DBG>(M, E, L, CL, q, v, tau, a, AS, Sj, dbgp);
+        pure_mass_column2<NV, G>(M, E, L, Sj, Hc);     // E.acc holds the constrained qacc of every dof
 #pragma unroll
         for (int r = 0; r < NV; r++) {
           if (DBG && dbgp) dbgp[(2 + r) * 32 + l] = Hc[r];
@@ -423,13 +434,14 @@ __global__ void __launch_bounds__(128, 4) mimic_step_kernel(const StepArgs A, co
     const bool blown = env_any(L.isdof && (!(fabsf(q) <= 1e10f) || !(fabsf(v) <= 1e10f)), L.emask);
     bad = bad || blown;
   }
-  if (bad) { q = L.ref; v = 0.f; a = 0.f; }
+  if (bad) { q = M.dof_ref[jd]; v = 0.f; a = 0.f; }
 
   // ---- environment logic (computed for every lane; the blow-up path overrides the outcome) ------------------------
   float walked = sf[3 * G + kMiscWalked];
   float ep_ret = sf[3 * G + kMiscEpRet], ep_tor = sf[3 * G + kMiscEpTor];
   float pos_rew = sf[3 * G + kMiscPrevPos], vel_rew = sf[3 * G + kMiscPrevVel], com_rew = sf[3 * G + kMiscPrevCom];
   float reward, phase0 = 0.f, des0 = 0.f;
+  float ov[2] = {0.f, 0.f};       // this lane's entries of the returned observation (fused VecNormalize moments)
   bool done;
   const int ep_dur_before = c.ep_dur;
   cursor_next(M, A, c, dist);                                   // mimic_env.py:96
@@ -490,27 +502,48 @@ __global__ void __launch_bounds__(128, 4) mimic_step_kernel(const StepArgs A, co
   {
     const bool left1 = M.mirror_policy && A.left_step[c.i_step];
     float* dst = (done && A.terminal_obs) ? A.terminal_obs + (size_t)env * M.obs_dim : obs_out;
-    write_obs<G>(M, E, l, left1, live && !bad, dst);
+    write_obs<G>(M, E, l, left1, live && !bad, dst, done ? nullptr : ov);
   }
+  // ---- per-environment row of sums for the step's statistics: [ sum obs[D] | sum obs^2[D] | ret, ret^2 | stats[20] ].
+  // It lives in this environment's (now dead) solver scratch; the rows of a thread block are added up in a fixed order
+  // at the end of the kernel, the blocks' rows by the last block to finish: no atomics, bit-reproducible sums.
+  const int kRowStats = 2 * M.obs_dim + 2, kRowLen = kRowStats + DRL_STATS_COUNT;
+  double* srow = reinterpret_cast<double*>(E.Mt);
+  for (int i = l; i < kRowLen; i += G) srow[i] = 0.0;
+  __syncwarp();
   // ---- Monitor.step (monitor_wrapper.py:88-166) --------------------------------------------------------------------
   ep_ret += reward;
   ep_tor += mean_abs_torque;
   double* sd = A.state_d + (size_t)env * 4;
   if (l == 0 && live) {
     sd[0] += (double)pos_rew; sd[1] += (double)vel_rew; sd[2] += (double)com_rew; sd[3] += 1.0;
-    atomicAdd(&A.stats[DRL_STAT_ENV_STEPS], 1.0);
-    atomicAdd(&A.stats[DRL_STAT_POS_REW_SUM], (double)pos_rew);
-    atomicAdd(&A.stats[DRL_STAT_VEL_REW_SUM], (double)vel_rew);
-    atomicAdd(&A.stats[DRL_STAT_COM_REW_SUM], (double)com_rew);
-    atomicAdd(&A.stats[DRL_STAT_REW_STEPS], 1.0);
-    atomicAdd(&A.stats[DRL_STAT_ABS_TORQUE_SUM], (double)mean_abs_torque);
-    atomicAdd(&A.stats[DRL_STAT_SOLVER_ITERS], (double)cnt.iters);
-    atomicAdd(&A.stats[DRL_STAT_DYN_EVALS], (double)cnt.evals);
-    if (cnt.capped) atomicAdd(&A.stats[DRL_STAT_SOLVER_CAPPED], (double)cnt.capped);
+    srow[kRowStats + DRL_STAT_ENV_STEPS] = 1.0;
+    srow[kRowStats + DRL_STAT_POS_REW_SUM] = (double)pos_rew;
+    srow[kRowStats + DRL_STAT_VEL_REW_SUM] = (double)vel_rew;
+    srow[kRowStats + DRL_STAT_COM_REW_SUM] = (double)com_rew;
+    srow[kRowStats + DRL_STAT_REW_STEPS] = 1.0;
+    srow[kRowStats + DRL_STAT_ABS_TORQUE_SUM] = (double)mean_abs_torque;
+    if constexpr (FDV == 2) {
+      srow[kRowStats + DRL_STAT_SOLVER_ITERS] = (double)E.cnt[0];
+      srow[kRowStats + DRL_STAT_DYN_EVALS] = (double)(A.frame_skip * (RK4 ? 4 : 1));
+      srow[kRowStats + DRL_STAT_SOLVER_CAPPED] = (double)E.cnt[1];
+    } else {
+      srow[kRowStats + DRL_STAT_SOLVER_ITERS] = (double)cnt.iters;
+      srow[kRowStats + DRL_STAT_DYN_EVALS] = (double)cnt.evals;
+      srow[kRowStats + DRL_STAT_SOLVER_CAPPED] = (double)cnt.capped;
+    }
     if (!bad) {
-      if (et_low) atomicAdd(&A.stats[DRL_STAT_ET_COM_LOW], 1.0);
-      if (et_trunk) atomicAdd(&A.stats[DRL_STAT_ET_TRUNK], 1.0);
-      if (et_drunk) atomicAdd(&A.stats[DRL_STAT_ET_DRUNK], 1.0);
+      srow[kRowStats + DRL_STAT_ET_COM_LOW] = et_low ? 1.0 : 0.0;
+      srow[kRowStats + DRL_STAT_ET_TRUNK] = et_trunk ? 1.0 : 0.0;
+      srow[kRowStats + DRL_STAT_ET_DRUNK] = et_drunk ? 1.0 : 0.0;
+    }
+    // VecNormalize: ret = ret * gamma + reward (SB3 VecNormalize.step_wait), its batch moments
+    // (ret[done] = 0 afterwards; the normalised reward itself is computed by drl_vecnorm_step from `rew`)
+    if (A.vn_ret) {
+      const float r = A.vn_ret[env] * A.vn_gamma + reward;
+      A.vn_ret[env] = done ? 0.f : r;
+      srow[2 * M.obs_dim] = (double)r;
+      srow[2 * M.obs_dim + 1] = (double)r * (double)r;
     }
     if (A.extras) {
       float* ex = A.extras + (size_t)env * 16;
@@ -534,12 +567,12 @@ __global__ void __launch_bounds__(128, 4) mimic_step_kernel(const StepArgs A, co
     smooth(kMiscTorSm, 1, ep_tor / (float)ep_len, 0.75f);
     c.flags |= 2;
     ms[kMiscMoved] = walked;
-    atomicAdd(&A.stats[DRL_STAT_EPISODES], 1.0);
-    atomicAdd(&A.stats[DRL_STAT_EP_LEN_SUM], (double)ep_len);
-    atomicAdd(&A.stats[DRL_STAT_EP_RET_SUM], (double)ep_ret);
-    if (ep_len > 1) atomicAdd(&A.stats[DRL_STAT_EP_MEAN_REW_SUM], (double)(ep_ret / (float)(ep_len - 1)));
-    atomicAdd(&A.stats[DRL_STAT_MOVED_DISTANCE_SUM], (double)walked);
-    atomicAdd(&A.stats[bad ? DRL_STAT_BLOWUPS : (timeout ? DRL_STAT_TIMEOUTS : DRL_STAT_FALLS)], 1.0);
+    srow[kRowStats + DRL_STAT_EPISODES] = 1.0;
+    srow[kRowStats + DRL_STAT_EP_LEN_SUM] = (double)ep_len;
+    srow[kRowStats + DRL_STAT_EP_RET_SUM] = (double)ep_ret;
+    if (ep_len > 1) srow[kRowStats + DRL_STAT_EP_MEAN_REW_SUM] = (double)(ep_ret / (float)(ep_len - 1));
+    srow[kRowStats + DRL_STAT_MOVED_DISTANCE_SUM] = (double)walked;
+    srow[kRowStats + (bad ? DRL_STAT_BLOWUPS : (timeout ? DRL_STAT_TIMEOUTS : DRL_STAT_FALLS))] = 1.0;
     if (A.ring_cap > 0) {
       const unsigned long long slot = atomicAdd(A.ring_head, 1ull) % (unsigned long long)A.ring_cap;
       A.ring_len[slot] = ep_len;
@@ -558,7 +591,7 @@ __global__ void __launch_bounds__(128, 4) mimic_step_kernel(const StepArgs A, co
     float ph, dv;
     build_obs<G>(M, A, E, L, c2, q2, v2, ph, dv);
     const bool left2 = M.mirror_policy && A.left_step[c2.i_step];
-    write_obs<G>(M, E, l, left2, live && done, obs_out);
+    write_obs<G>(M, E, l, left2, live && done, obs_out, ov);
     write_obs<G>(M, E, l, left2, live && bad && A.terminal_obs != nullptr,
                  A.terminal_obs ? A.terminal_obs + (size_t)env * M.obs_dim : obs_out);
     if (done) {
@@ -582,6 +615,66 @@ __global__ void __launch_bounds__(128, 4) mimic_step_kernel(const StepArgs A, co
       ms[kMiscEpTor] = ep_tor; ms[kMiscPrevPos] = pos_rew; ms[kMiscPrevVel] = vel_rew; ms[kMiscPrevCom] = com_rew;
       si[kCurIstep] = c.i_step; si[kCurPos] = c.pos; si[kCurCount] = c.count; si[kCurEpDur] = c.ep_dur;
       si[kCurRsiStep] = c.rsi_step; si[kCurNDet] = c.n_det; si[kCurResets] = c.resets; si[kCurFlags] = c.flags;
+    }
+  }
+  // ---- statistics of the step: obs moments of the returned observation, then block sum, then grid sum ---------------
+  if (live) {
+#pragma unroll
+    for (int t = 0; t < 2; t++) {
+      const int k = l + t * G;
+      if (k < M.obs_dim) {
+        const double x = (double)ov[t];
+        srow[k] = x;
+        srow[M.obs_dim + k] = x * x;
+      }
+    }
+  }
+  __syncthreads();
+  {
+    // rows of this block's environments, added in environment order
+    double* rows0 = reinterpret_cast<double*>(envs[0].Mt);
+    const size_t estride = sizeof(ES) / sizeof(double);
+    for (int col = threadIdx.x; col < kRowLen; col += blockDim.x) {
+      double sum = 0.0;
+      for (int e = 0; e < epb; e++) sum += rows0[(size_t)e * estride + col];
+      A.cta_rows[(size_t)blockIdx.x * kRowLen + col] = sum;
+    }
+  }
+  __threadfence();
+  __syncthreads();
+  __shared__ unsigned s_ticket;
+  if (threadIdx.x == 0) s_ticket = atomicAdd(A.cta_ticket, 1u);
+  __syncthreads();
+  if (s_ticket == gridDim.x - 1) {
+    // the last block to finish adds up the blocks' rows, again in a fixed order (four interleaved partial sums per
+    // column keep the loads in flight), and publishes: batch moments -> A.packed, statistics -> added to A.stats
+    __threadfence();
+    const int nrows = (int)gridDim.x;
+    for (int col = threadIdx.x; col < kRowLen; col += blockDim.x) {
+      double p0 = 0.0, p1 = 0.0, p2 = 0.0, p3 = 0.0;
+      const double* src = A.cta_rows + col;
+      int r = 0;
+      for (; r + 3 < nrows; r += 4) {
+        p0 += __ldcg(src + (size_t)r * kRowLen);
+        p1 += __ldcg(src + (size_t)(r + 1) * kRowLen);
+        p2 += __ldcg(src + (size_t)(r + 2) * kRowLen);
+        p3 += __ldcg(src + (size_t)(r + 3) * kRowLen);
+      }
+      for (; r < nrows; r++) p0 += __ldcg(src + (size_t)r * kRowLen);
+      const double tot = (p0 + p1) + (p2 + p3);
+      if (col < kRowStats) {
+        if (A.packed) {
+          // packed layout of the VecNormalize kernels: [ sum obs[D], sumsq obs[D], n, sum ret, sumsq ret ]
+          const int D = M.obs_dim;
+          A.packed[col < 2 * D ? col : col + 1] = tot;
+        }
+      } else {
+        A.stats[col - kRowStats] += tot;
+      }
+    }
+    if (threadIdx.x == 0) {
+      if (A.packed) A.packed[2 * M.obs_dim] = (double)A.num_envs;
+      *A.cta_ticket = 0u;
     }
   }
 }

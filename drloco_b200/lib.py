@@ -36,11 +36,19 @@ PROTOTYPES = {
     "drl_set_eval_mode": (C.c_int, [vp, i32]),
     "drl_set_det_init_counters": (C.c_int, [vp, vp]),
     "drl_set_speed_profile": (C.c_int, [vp, vp, i32]),
+    "drl_set_seed": (C.c_int, [vp, C.c_uint64]),
     "drl_set_playback": (C.c_int, [vp, i32]),
     "drl_launch_info": (C.c_int, [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]),
     "drl_debug_set": (C.c_int, [vp, i32, i32, i32]),
     "drl_debug_read": (C.c_int, [vp, vp, i32]),
+    "drl_attach_vecnorm": (C.c_int, [vp, vp, f32, vp]),
+    "drl_comm_create": (C.c_int, [i32, i32, i32, C.POINTER(vp)]),
+    "drl_comm_export": (C.c_int, [vp, vp]),
+    "drl_comm_connect": (C.c_int, [vp, vp]),
+    "drl_comm_destroy": (C.c_int, [vp]),
+    "drl_vecnorm_step": (C.c_int, [vp, vp, vp, vp, i32, i32, vp, vp, vp, vp, vp, f32, f32, f32, i32, vp, i32, vp]),
     "drl_vecnorm_terminal": (C.c_int, [vp, vp, vp, i32, i32, vp, f32, f32, i32, vp]),
+    "drl_vecnorm_terminal_compact": (C.c_int, [vp, vp, i32, i32, vp, f32, f32, i32, vp, vp]),
     "drl_fp32_peak_probe": (C.c_int, [i32, C.POINTER(C.c_double)]),
     "drl_vecnorm_moments": (C.c_int, [vp, i32, i32, vp, vp, f32, vp, vp]),
     "drl_vecnorm_apply": (C.c_int, [vp, vp, vp, vp, i32, i32, vp, vp, vp, vp, vp, f32, f32, f32, i32, vp]),

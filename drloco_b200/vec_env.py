@@ -13,6 +13,7 @@ Two ways to step:
 from __future__ import annotations
 
 import ctypes as C
+from collections.abc import Sequence
 from typing import Any, List, Optional, Tuple
 
 import numpy as np
@@ -38,6 +39,79 @@ class Box:
 
     def __repr__(self):
         return f"Box({self.low.min()}, {self.high.max()}, {self.shape}, {self.dtype})"
+
+
+class LazyInfos(Sequence):
+    """``infos`` of a step: behaves like the list of per-env dicts SB3's VecEnv returns, but only the finished
+    environments own a dict up front (``{"terminal_observation": ...}``); any other entry is created (and remembered) the
+    first time it is touched.  Nothing is shared between entries or between steps."""
+
+    __slots__ = ("_n", "_d")
+
+    def __init__(self, n: int, filled: Optional[dict] = None):
+        self._n, self._d = n, filled if filled is not None else {}
+
+    def __len__(self):
+        return self._n
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self[j] for j in range(*i.indices(self._n))]
+        i = int(i)
+        if i < 0:
+            i += self._n
+        if not 0 <= i < self._n:
+            raise IndexError(i)
+        d = self._d.get(i)
+        if d is None:
+            d = self._d[i] = {}
+        return d
+
+    def __iter__(self):
+        return (self[i] for i in range(self._n))
+
+    def __eq__(self, other):
+        return len(other) == self._n and all(a == b for a, b in zip(self, other))
+
+    def __repr__(self):
+        return f"LazyInfos(n={self._n}, filled={sorted(self._d)})"
+
+
+class _TerminalRows:
+    """device -> host path of the terminal observations: the rows of finished environments are compacted on the device
+    (csrc/vecnorm.cu::vecnorm_terminal_compact_kernel) and a fixed-size prefix of the record buffer travels with the
+    step's other outputs; the rest is fetched only when more environments finished than the prefix holds."""
+
+    PREFIX = 256
+
+    def __init__(self, n: int, d: int, device):
+        self.n, self.d, self.device = n, d, device
+        self.words = 4 + n * (d + 1)
+        self.dev = torch.zeros(self.words, dtype=torch.float32, device=device)
+        self.npre = 4 + min(n, self.PREFIX) * (d + 1)
+        self.host = torch.zeros(self.words, dtype=torch.float32).pin_memory()
+        self.host_np = self.host.numpy()
+        self.host_i = self.host_np.view(np.int32)
+
+    def enqueue(self, libh, tobs, done, rms, clip_obs, eps, norm_obs, stream_ptr):
+        lib.check(libh.drl_vecnorm_terminal_compact(_ptr(tobs), _ptr(done), self.n, self.d, _ptr(rms), float(clip_obs),
+                                                    float(eps), int(norm_obs), _ptr(self.dev), stream_ptr),
+                  "drl_vecnorm_terminal_compact")
+        self.host[:self.npre].copy_(self.dev[:self.npre], non_blocking=True)
+
+    def collect(self, dtype) -> dict:
+        """after the stream has been synchronised: {env index: terminal observation}"""
+        cnt = int(self.host_i[0])
+        if cnt == 0:
+            return {}
+        need = 4 + cnt * (self.d + 1)
+        if need > self.npre:
+            self.host[self.npre:need].copy_(self.dev[self.npre:need], non_blocking=True)
+            torch.cuda.current_stream(self.device).synchronize()
+        rec = self.host_np[4:need].reshape(cnt, self.d + 1)
+        idx = self.host_i[4:need].reshape(cnt, self.d + 1)[:, 0]
+        rows = rec[:, 1:].astype(dtype)                  # one copy = fresh memory for all terminal observations
+        return {int(i): {"terminal_observation": rows[k]} for k, i in enumerate(idx.tolist())}
 
 
 def _ptr(t: Optional[torch.Tensor]):
@@ -86,9 +160,9 @@ class B200MimicVecEnv:
             # pinned staging for the numpy API
             self._h_act = torch.zeros(N, self.act_dim).pin_memory()
             self._h_obs = torch.zeros(N, D).pin_memory()
-            self._h_tobs = torch.zeros(N, D).pin_memory()
             self._h_rew = torch.zeros(N).pin_memory()
             self._h_done = torch.zeros(N, dtype=torch.uint8).pin_memory()
+            self._trows = _TerminalRows(N, D, dev)
         self._inj = None
         self._pending = False
         self._ep_lens_base = 0        # set_attr('ep_lens', []) marks the ring position (callback.py:69-70)
@@ -194,7 +268,9 @@ class B200MimicVecEnv:
         self._h_obs.copy_(self.obs, non_blocking=True)
         self._h_rew.copy_(self.rew, non_blocking=True)
         self._h_done.copy_(self.done, non_blocking=True)
-        self._h_tobs.copy_(self.terminal_obs, non_blocking=True)
+        with torch.cuda.device(self.device):
+            self._trows.enqueue(self._lib, self.terminal_obs, self.done, None, 0.0, 0.0, 0, self._stream())
+        self.launches += 1
         self._pending = True
 
     def step_wait(self):
@@ -205,11 +281,7 @@ class B200MimicVecEnv:
         obs = self._h_obs.numpy().astype(np.float64)
         rew = self._h_rew.numpy().astype(np.float64)
         done = self._h_done.numpy().astype(bool)
-        infos: List[dict] = [{} for _ in range(self.num_envs)]
-        if done.any():
-            tobs = self._h_tobs.numpy()
-            for i in np.nonzero(done)[0]:
-                infos[i]["terminal_observation"] = tobs[i].astype(np.float64)
+        infos = LazyInfos(self.num_envs, self._trows.collect(np.float64))
         return obs, rew, done, infos
 
     def step(self, actions, inject=None):
@@ -229,8 +301,13 @@ class B200MimicVecEnv:
             pass
 
     def seed(self, seed: Optional[int] = None):
-        """The RSI stream is keyed at construction (counter-based generator); kept for interface compatibility."""
-        return [None if seed is None else seed + i for i in range(self.num_envs)]
+        """``VecEnv.seed``: the reference calls ``env.seed(seed + rank * 100)`` when it builds its workers
+        (utils.py:113).  Here it re-keys the counter-based RSI generator: env i then draws
+        ``splitmix64(seed, env_id_offset + i, reset #)``.  Returns the per-env seeds as SB3 does."""
+        if seed is None:
+            return [None] * self.num_envs
+        lib.check(self._lib.drl_set_seed(self._handle, C.c_uint64(int(seed) & (2 ** 64 - 1))), "drl_set_seed")
+        return [int(seed) + i for i in range(self.num_envs)]
 
     def env_is_wrapped(self, wrapper_class, indices=None):
         return [False] * len(self._indices(indices))
@@ -429,17 +506,34 @@ class RunningMeanStdView:
 
 class B200VecNormalize:
     """SB3 VecNormalize semantics on the device (utils.py:130-132: norm_obs=True, norm_reward=norm_rew, clip 10/10,
-    gamma=0.99, epsilon=1e-8).  With ``torch.distributed`` initialised, the packed batch moments are all-reduced
-    (NCCL) so that every rank holds identical running statistics."""
+    gamma=0.99, epsilon=1e-8), fused with the env: the step kernel itself keeps ``ret = ret*gamma + rew`` and leaves the
+    batch moments of the observations it returns (csrc/mimic_step.cu epilogue, fixed-order sums: bit-reproducible), and
+    ONE more kernel (csrc/vecnorm.cu::vecnorm_step_kernel) merges them into the running statistics and normalises.
+
+    With ``torch.distributed`` initialised (one process per GPU of a node) the ranks' moments are exchanged inside that
+    kernel through peer-mapped mailboxes over NVLink (``exchange="peer"``): no host-issued collective sits between the
+    env step and the normalised observation.  ``exchange="nccl"`` keeps the all-reduce (ranks on different nodes, or
+    no peer access).  Either way every rank holds bit-identical running statistics.
+
+    ``stats_sync_every=K`` (opt-in, not SB3 semantics): exchange and merge the accumulated moments on every K-th step
+    only; the steps in between are normalised with the statistics of the last merge.
+
+    ``reset_update``: what ``reset()`` does to the statistics.  "sb3-1.0" (default) is SB3 1.0's ``VecNormalize.reset``:
+    ``ret = 0`` and ``ret_rms.update(zeros)``, observation statistics untouched; "obs" also feeds the reset observations
+    to ``obs_rms`` (later SB3 releases).  SB3 is not installed here: both are restated from memory.
+    """
 
     def __init__(self, venv: B200MimicVecEnv, training=True, norm_obs=True, norm_reward=True, clip_obs=10.0,
                  clip_reward=10.0, gamma=0.99, epsilon=1e-8, distributed: Optional[bool] = None,
-                 stats_sync_every: int = 1):
+                 stats_sync_every: int = 1, exchange: str = "auto", reset_update: str = "sb3-1.0"):
+        if reset_update not in ("sb3-1.0", "obs"):
+            raise ValueError("reset_update must be 'sb3-1.0' or 'obs'")
         self.venv = venv
         self.num_envs, self.device = venv.num_envs, venv.device
         self.observation_space, self.action_space = venv.observation_space, venv.action_space
         self.training, self.norm_obs, self.norm_reward = training, norm_obs, norm_reward
         self.clip_obs, self.clip_reward, self.gamma, self.epsilon = clip_obs, clip_reward, gamma, epsilon
+        self.reset_update = reset_update
         D = venv.obs_dim
         self._D = D
         dev = self.device
@@ -450,13 +544,15 @@ class B200VecNormalize:
         rms[2 * D + 3] = 1e-4
         self._rms = [rms, rms.clone()]
         self._cur = 0
-        self._packed = torch.zeros(2 * D + 3, dtype=torch.float64, device=dev)
+        # batch moments of a step, written by the step kernel; one buffer per env output set
+        self._packed = [torch.zeros(2 * D + 3, dtype=torch.float64, device=dev) for _ in range(2)]
+        self._packed_reset = torch.zeros(2 * D + 3, dtype=torch.float64, device=dev)
         self.ret = torch.zeros(self.num_envs, device=dev)
         self._nobs = [torch.zeros(self.num_envs, D, device=dev) for _ in range(2)]
         self._nrew = [torch.zeros(self.num_envs, device=dev) for _ in range(2)]
         self._k = 0
-        # the statistics / normalisation chain (two kernels + the all-reduce) runs on a side stream so that it can
-        # overlap the next env step when the caller does not consume the normalised tensors immediately
+        # the normalisation kernel runs on a side stream so that it can overlap the next env step when the caller does
+        # not consume the normalised tensors immediately
         with torch.cuda.device(dev):
             self._side = torch.cuda.Stream(device=dev)
             self._done_ev = [torch.cuda.Event(), torch.cuda.Event()]
@@ -466,9 +562,52 @@ class B200VecNormalize:
                 and torch.distributed.get_world_size() > 1
         self.distributed = distributed
         self.stats_sync_every = max(1, int(stats_sync_every))
-        self._since_sync = 0
         self._lib = venv._lib
         self.launches = 0
+        self._calls = 0                        # normalisation calls so far (host mirror of the device step counter)
+        self._pending = None                   # exchange == "nccl" with stats_sync_every > 1: host-managed accumulation
+        self._comm = C.c_void_p()
+        self.exchange = self._setup_exchange(exchange)
+        lib.check(self._lib.drl_attach_vecnorm(venv._handle, _ptr(self.ret), float(self.gamma),
+                                               _ptr(self._packed[0])), "drl_attach_vecnorm")
+
+    # -- statistics exchange ------------------------------------------------------------------------
+    def _setup_exchange(self, mode: str) -> str:
+        """"peer": mailboxes in every rank's HBM, mapped by the peers through CUDA IPC (one node, NVLink);
+        "nccl": all-reduce of the packed moments; "local": single process."""
+        dist = torch.distributed
+        world = dist.get_world_size() if self.distributed else 1
+        rank = dist.get_rank() if self.distributed else 0
+        if mode not in ("auto", "peer", "nccl"):
+            raise ValueError("exchange must be 'auto', 'peer' or 'nccl'")
+        want_peer = world > 1 and mode in ("auto", "peer") and world <= 8
+        with torch.cuda.device(self.device):
+            if want_peer:
+                comm = C.c_void_p()
+                lib.check(self._lib.drl_comm_create(world, rank, self._D, C.byref(comm)), "drl_comm_create")
+                handle = torch.zeros(64, dtype=torch.uint8)
+                ok = self._lib.drl_comm_export(comm, C.c_void_p(handle.data_ptr())) == 0
+                # every rank learns every handle (and whether every rank could export one)
+                mine = torch.cat([handle, torch.tensor([1 if ok else 0], dtype=torch.uint8)]).to(self.device)
+                allh = [torch.zeros_like(mine) for _ in range(world)]
+                dist.all_gather(allh, mine)
+                allh = torch.stack(allh).cpu()
+                ok = bool(allh[:, 64].all())
+                if ok:
+                    table = allh[:, :64].contiguous()
+                    ok = self._lib.drl_comm_connect(comm, C.c_void_p(table.data_ptr())) == 0
+                flag = torch.tensor([1 if ok else 0], device=self.device)
+                dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+                if int(flag.item()) == 1:
+                    self._comm = comm
+                    return "peer"
+                self._lib.drl_comm_destroy(comm)
+                if mode == "peer":
+                    raise lib.DrlError("exchange='peer': CUDA IPC peer mapping is not available between these ranks")
+            comm = C.c_void_p()
+            lib.check(self._lib.drl_comm_create(1, 0, self._D, C.byref(comm)), "drl_comm_create")
+            self._comm = comm
+        return "nccl" if world > 1 else "local"
 
     # -- SB3 attribute surface ----------------------------------------------------------------------
     @property
@@ -483,43 +622,58 @@ class B200VecNormalize:
         r, D = self._rms[self._cur], self._D
         return RunningMeanStdView(float(r[2 * D + 1]), float(r[2 * D + 2]), float(r[2 * D + 3]))
 
-    def _flags(self):
-        return (1 if self.training else 0) | (2 if self.norm_obs else 0) | (4 if self.norm_reward else 0)
-
     norm_obs_buf = property(lambda self: self._nobs[self._k])
     norm_rew_buf = property(lambda self: self._nrew[self._k])
 
-    def _normalize(self, obs, rew, done, wait=True):
-        """enqueue moments -> (all-reduce) -> apply for the env outputs just produced on the current stream.
-        wait=True makes the current stream wait for the result (normal use); wait=False leaves the chain running on
-        the side stream (``synchronize()`` / the next ``wait=True`` call / a stream sync picks it up)."""
-        v = self.venv
+    def _attach_next(self):
+        """the step about to be enqueued writes its moments into the buffer paired with the env's next output set"""
+        lib.check(self._lib.drl_attach_vecnorm(self.venv._handle, _ptr(self.ret), float(self.gamma),
+                                               _ptr(self._packed[self._k ^ 1])), "drl_attach_vecnorm")
+
+    def _normalize(self, obs, rew, done, wait=True, packed=None, upd_obs=None, upd_ret=None):
+        """enqueue the exchange + merge + normalisation kernel for the env outputs just produced on the current stream.
+        wait=True makes the current stream wait for the result (normal use); wait=False leaves it running on the side
+        stream (``synchronize()`` / the next ``wait=True`` call / a stream sync picks it up)."""
         main = torch.cuda.current_stream(self.device)
         self._k ^= 1
         k = self._k
         nobs, nrew = self._nobs[k], self._nrew[k]
+        if packed is None:
+            packed = self._packed[k]
+        upd_obs = self.training if upd_obs is None else upd_obs
+        upd_ret = (self.training and rew is not None) if upd_ret is None else upd_ret
+        K = self.stats_sync_every
         ready = torch.cuda.Event()
         ready.record(main)
         with torch.cuda.device(self.device), torch.cuda.stream(self._side):
             self._side.wait_event(ready)
-            st = v._stream()
-            packed = None
-            if self.training:
-                lib.check(self._lib.drl_vecnorm_moments(_ptr(obs), self.num_envs, self._D, _ptr(rew),
-                                                        _ptr(self.ret) if rew is not None else None,
-                                                        float(self.gamma), _ptr(self._packed), st), "drl_vecnorm_moments")
-                self.launches += 1
-                if self.distributed:
-                    torch.distributed.all_reduce(self._packed, op=torch.distributed.ReduceOp.SUM)
-                packed = self._packed
+            sync_every = K
+            if self.exchange == "nccl" and (upd_obs or upd_ret):
+                # host-issued collective: the kernel then sees a single-rank exchange of already reduced moments
+                sync_every = 1
+                if K > 1:
+                    if self._pending is None:
+                        self._pending = torch.zeros_like(packed)
+                    self._pending += packed
+                    if (self._calls + 1) % K == 0:
+                        packed = self._pending.clone()
+                        self._pending.zero_()
+                    else:
+                        upd_obs = upd_ret = False
+                if upd_obs or upd_ret:
+                    if packed is self._packed[k] or packed is self._packed_reset:
+                        packed = packed.clone()
+                    torch.distributed.all_reduce(packed, op=torch.distributed.ReduceOp.SUM)
+            flags = (1 if upd_obs else 0) | (2 if self.norm_obs else 0) | (4 if self.norm_reward else 0) | \
+                (8 if upd_ret else 0)
             src, dst = self._rms[self._cur], self._rms[1 - self._cur]
-            lib.check(self._lib.drl_vecnorm_apply(_ptr(obs), _ptr(nobs), _ptr(rew),
-                                                  _ptr(nrew) if rew is not None else None,
-                                                  self.num_envs, self._D, _ptr(packed), _ptr(src), _ptr(dst),
-                                                  _ptr(self.ret), _ptr(done), float(self.clip_obs),
-                                                  float(self.clip_reward), float(self.epsilon), self._flags(), st),
-                      "drl_vecnorm_apply")
+            lib.check(self._lib.drl_vecnorm_step(_ptr(obs), _ptr(nobs), _ptr(rew), _ptr(nrew) if rew is not None else None,
+                                                 self.num_envs, self._D, _ptr(packed), _ptr(src), _ptr(dst),
+                                                 _ptr(self.ret), _ptr(done), float(self.clip_obs),
+                                                 float(self.clip_reward), float(self.epsilon), flags, self._comm,
+                                                 int(sync_every), self.venv._stream()), "drl_vecnorm_step")
             self.launches += 1
+            self._calls += 1
             self._cur = 1 - self._cur
             self._done_ev[k].record(self._side)
             self._ev_used[k] = True
@@ -543,38 +697,51 @@ class B200VecNormalize:
         self.synchronize()
         obs = self.venv.reset_tensor(None, inject)
         self.ret.zero_()
-        self._normalize(obs, None, None)
+        D = self._D
+        if self.reset_update == "obs":
+            # the reset observations update obs_rms (their moments come from the stand-alone moments kernel: the reset
+            # launch has no statistics epilogue)
+            pk = self._packed_reset
+            with torch.cuda.device(self.device):
+                lib.check(self._lib.drl_vecnorm_moments(_ptr(obs), self.num_envs, D, None, None, float(self.gamma),
+                                                        _ptr(pk), self.venv._stream()), "drl_vecnorm_moments")
+            self.launches += 1
+            self._normalize(obs, None, None, packed=pk, upd_obs=self.training, upd_ret=False)
+        else:
+            # SB3 1.0 VecNormalize.reset: self.ret = zeros; if training: ret_rms.update(self.ret)
+            pk = self._packed_reset
+            pk.zero_()
+            pk[2 * D] = float(self.num_envs)
+            self._normalize(obs, None, None, packed=pk, upd_obs=False, upd_ret=self.training)
         return self.norm_obs_buf
 
     def step_tensor(self, actions, inject=None, wait=True):
         self._guard_reuse()
+        self._attach_next()
         obs, rew, done = self.venv.step_tensor(actions, inject)
         self._normalize(obs, rew, done, wait)
         return self.norm_obs_buf, self.norm_rew_buf, done
 
     # -- SB3 numpy API -----------------------------------------------------------------------------------
     # float32 arrays are returned (SB3 converts observations to float32 tensors anyway).  Actions go through a pinned
-    # staging buffer; obs / reward / done come back with one asynchronous copy each and ONE event wait; the terminal
-    # observations follow on a second event that is only waited for when an episode ended (their copy overlaps the
-    # host-side post-processing).  The returned observation array is a view of one of two alternating pinned buffers:
-    # it stays valid until the second following `step` (SB3's collect_rollouts reads `_last_obs` during the next step
-    # and stores it right after - that is covered); copy it to keep it longer.  `copy_outputs=True` restores copies.
-    copy_outputs = False
+    # staging buffer; obs / reward / done and a fixed-size prefix of the compacted terminal observations come back with
+    # one asynchronous copy each and ONE stream synchronisation.  By default every returned array is a fresh copy.
+    # `copy_outputs = False` hands out views of two alternating pinned buffers instead (valid until the second
+    # following `step`; SB3's collect_rollouts reads `_last_obs` during the next step and stores it right after, which
+    # that covers) and saves one 0.5 MB host copy per step.
+    copy_outputs = True
 
     def _host_buffers(self):
         if not hasattr(self, "_h"):
             N, D, A = self.num_envs, self._D, self.venv.act_dim
             self._h = dict(act=torch.zeros(N, A).pin_memory(),
                            obs=[torch.zeros(N, D).pin_memory() for _ in range(2)],
-                           rew=torch.zeros(N).pin_memory(), done=torch.zeros(N, dtype=torch.uint8).pin_memory(),
-                           tobs=torch.zeros(N, D).pin_memory())
+                           rew=torch.zeros(N).pin_memory(), done=torch.zeros(N, dtype=torch.uint8).pin_memory())
             self._h_np = dict(act=self._h["act"].numpy(), obs=[t.numpy() for t in self._h["obs"]],
-                              rew=self._h["rew"].numpy(), done=self._h["done"].numpy(), tobs=self._h["tobs"].numpy())
+                              rew=self._h["rew"].numpy(), done=self._h["done"].numpy())
             self._hk = 0
             self._d_act = torch.zeros(N, A, device=self.device)
-            self._d_ntobs = torch.zeros(N, D, device=self.device)
-            self._no_info = [{} for _ in range(N)]
-            self._ev_out, self._ev_tobs = torch.cuda.Event(), torch.cuda.Event()
+            self._trows = _TerminalRows(N, D, self.device)
         return self._h
 
     def reset(self, inject=None):
@@ -594,34 +761,31 @@ class B200VecNormalize:
         h["obs"][self._hk].copy_(obs, non_blocking=True)
         h["rew"].copy_(rew, non_blocking=True)
         h["done"].copy_(done, non_blocking=True)
-        stream = torch.cuda.current_stream(self.device)
-        self._ev_out.record(stream)
         with torch.cuda.device(self.device):
-            lib.check(self._lib.drl_vecnorm_terminal(_ptr(self.venv.terminal_obs), _ptr(self._d_ntobs), _ptr(done),
-                                                     self.num_envs, self._D, _ptr(self._rms[self._cur]),
-                                                     float(self.clip_obs), float(self.epsilon), int(self.norm_obs),
-                                                     self.venv._stream()), "drl_vecnorm_terminal")
+            # terminal observations normalised with the statistics just merged (SB3 VecNormalize.step_wait)
+            self._trows.enqueue(self._lib, self.venv.terminal_obs, done, self._rms[self._cur], self.clip_obs,
+                                self.epsilon, self.norm_obs, self.venv._stream())
         self.launches += 1
-        h["tobs"].copy_(self._d_ntobs, non_blocking=True)
-        self._ev_tobs.record(stream)
 
     def step_wait(self):
         hn = self._h_np
-        self._ev_out.synchronize()
+        torch.cuda.current_stream(self.device).synchronize()
         done = hn["done"].astype(bool)
-        infos = list(self._no_info)
-        idx = np.flatnonzero(done)
-        if idx.size:
-            self._ev_tobs.synchronize()
-            rows = hn["tobs"][idx]                       # one gather = fresh memory for all terminal observations
-            for k, i in enumerate(idx.tolist()):
-                infos[i] = {"terminal_observation": rows[k]}
+        infos = LazyInfos(self.num_envs, self._trows.collect(np.float32))
         obs = hn["obs"][self._hk]
         return (obs.copy() if self.copy_outputs else obs), hn["rew"].copy(), done, infos
 
     def step(self, actions, inject=None):
         self.step_async(actions, inject)
         return self.step_wait()
+
+    def h2d_bytes_per_step(self) -> int:
+        return self.num_envs * self.venv.act_dim * 4
+
+    def d2h_bytes_per_step(self) -> int:
+        """obs + reward + done + the terminal-record prefix (more only when > _TerminalRows.PREFIX envs finish)"""
+        self._host_buffers()
+        return self.num_envs * (self._D * 4 + 4 + 1) + self._trows.npre * 4
 
     def normalize_obs(self, obs: torch.Tensor) -> torch.Tensor:
         if not self.norm_obs:
@@ -680,6 +844,8 @@ class B200VecNormalize:
             sd = read_sb3_vecnormalize(path)
         vn = B200VecNormalize(venv)
         vn.load_state_dict(sd)
+        if "training" in sd:                      # SB3's VecNormalize.load restores the pickled flag
+            vn.training = bool(sd["training"])
         return vn
 
     # -- pass-through ----------------------------------------------------------------------------------------
@@ -699,6 +865,11 @@ class B200VecNormalize:
         return self.venv.env_is_wrapped(wrapper_class, indices)
 
     def close(self):
+        if self._comm:
+            torch.cuda.synchronize(self.device)
+            self._lib.drl_attach_vecnorm(self.venv._handle, None, 0.0, None)
+            self._lib.drl_comm_destroy(self._comm)
+            self._comm = C.c_void_p()
         self.venv.close()
 
 

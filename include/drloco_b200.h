@@ -215,6 +215,10 @@ int drl_set_eval_mode(DrlEnv* env, int32_t on);
  * (callback.py:296-297).  Synchronises the device. */
 int drl_set_det_init_counters(DrlEnv* env, const int32_t* counts);
 
+/* VecEnv.seed - the reference seeds every worker env with seed + rank*100 when it builds them (utils.py:113).  Re-keys the
+ * counter-based RSI generator: env i draws splitmix64(seed, env_id_offset + i, reset #).  Synchronises the device. */
+int drl_set_seed(DrlEnv* env, uint64_t seed);
+
 /* MimicEnv.activate_speed_control (mimic_env.py:298-327): from now on the desired-velocity observation of every env is
  * speeds[ep_dur % n] (mimic_env.py:406-408) and resets use the deterministic init state (mimic_env.py:536-537).
  * `speeds` is a HOST array with one desired speed per control step (the host builds it with the reference's
@@ -246,10 +250,45 @@ int drl_vecnorm_apply(const float* obs_in, float* obs_out, const float* rew_in, 
                       const double* packed, const double* rms_in, double* rms_out, float* ret, const uint8_t* done,
                       float clip_obs, float clip_rew, float eps, int32_t flags, void* stream);
 
+/* Fused VecNormalize path (what B200VecNormalize uses): ONE kernel per step after drl_step.
+ *
+ * drl_attach_vecnorm: from now on drl_step itself maintains ret = ret*gamma + rew (device float [N], in/out) and leaves
+ *   the batch moments of the step in packed (device double [2*obs_dim+3], layout as drl_vecnorm_moments) - computed in
+ *   the step kernel's epilogue from the observations it returns, block sums then a fixed-order grid sum, no atomics:
+ *   the moments (and the Monitor statistics, drl_get_stats) are bit-reproducible.  Two NULLs detach.
+ * DrlComm: the statistics exchange between the ranks of one node (one process per GPU) without a host-issued
+ *   collective - replaces the all-reduce of SB3-style data-parallel VecNormalize statistics.
+ *   Every rank creates one (current CUDA device), publishes its 64-byte CUDA IPC handle (drl_comm_export), gathers the
+ *   handles of all ranks by any means (torch.distributed.all_gather) and maps its peers' mailboxes (drl_comm_connect,
+ *   handles = world x 64 bytes in rank order).  world == 1 needs no export / connect.
+ * drl_vecnorm_step: exchange (peer stores into the mailboxes over NVLink + flags, summed in rank order: identical bits
+ *   on every rank) + Chan merge into rms (rms_in -> rms_out, must not alias) + normalisation of obs / rew +
+ *   ret[done] = 0.  flags: bit0 update the observation statistics, bit1 norm_obs, bit2 norm_reward, bit3 update the
+ *   return statistics.  packed == NULL or no update bit: normalise only.  sync_every = K > 1 accumulates the moments
+ *   locally and exchanges / merges on every K-th call only (opt-in amortisation; SB3 merges every step).  All ranks
+ *   must make the same sequence of calls.  Asynchronous on `stream`; CUDA-graph capturable (the step counter lives on
+ *   the device). */
+typedef struct DrlComm DrlComm;
+int drl_attach_vecnorm(DrlEnv* env, float* ret, float gamma, double* packed);
+int drl_comm_create(int32_t world, int32_t rank, int32_t obs_dim, DrlComm** out);
+int drl_comm_export(DrlComm* comm, void* handle64);
+int drl_comm_connect(DrlComm* comm, const void* handles);
+int drl_comm_destroy(DrlComm* comm);
+int drl_vecnorm_step(const float* obs_in, float* obs_out, const float* rew_in, float* rew_out, int32_t n, int32_t d,
+                     const double* packed, const double* rms_in, double* rms_out, float* ret, const uint8_t* done,
+                     float clip_obs, float clip_rew, float eps, int32_t flags, DrlComm* comm, int32_t sync_every,
+                     void* stream);
+
 /* rows of tobs_in whose done byte is set, normalised with rms ({mean[d], var[d], ...}) into tobs_out: the
  * infos[i]["terminal_observation"] VecNormalize returns (SB3 VecNormalize.step_wait). Other rows are left untouched. */
 int drl_vecnorm_terminal(const float* tobs_in, float* tobs_out, const uint8_t* done, int32_t n, int32_t d,
                          const double* rms, float clip_obs, float eps, int32_t norm_obs, void* stream);
+
+/* the same, compacted on the device so that only finished environments cross PCIe: out_words (device, 4 + n*(d+1) 32-bit
+ * words) = header { count, 0, 0, 0 } + one record { env index (int32), d floats } per finished environment, in
+ * arbitrary order.  rms may be NULL when norm_obs == 0 (raw terminal observations). */
+int drl_vecnorm_terminal_compact(const float* tobs_in, const uint8_t* done, int32_t n, int32_t d, const double* rms,
+                                 float clip_obs, float eps, int32_t norm_obs, float* out_words, void* stream);
 
 /* measured sustained FFMA rate of `device` in TFLOP/s (8 independent FMA chains per thread, all SMs): the FP32
  * roofline denominator bench.py reports next to the HBM one. Synchronises the device. */

@@ -437,9 +437,14 @@ class OracleVecNormalize:
         self.ret[dones] = 0
         return nobs, nrew, dones, infos
 
-    def reset(self, **kw):
+    def reset(self, reset_update="sb3-1.0", **kw):
+        """SB3 1.0 VecNormalize.reset (restated from memory; SB3 is absent here): ``self.ret = zeros``, then
+        ``self._update_reward(self.ret)`` when training - the observation statistics are NOT updated at reset in that
+        release.  reset_update="obs" is the later behaviour (obs_rms.update(obs) as well)."""
         obs = self.venv.reset(**kw)
         self.ret = np.zeros(self.venv.num_envs)
         if self.training:
-            self.obs_rms.update(obs)
+            self.ret_rms.update(self.ret)
+            if reset_update == "obs":
+                self.obs_rms.update(obs)
         return self.normalize_obs(obs)

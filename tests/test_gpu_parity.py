@@ -588,7 +588,7 @@ def test_vecnormalize_matches_sb3_semantics():
     rng = np.random.default_rng(4)
     o = vn.reset()
     raw = env.obs.cpu().numpy().astype(np.float64)
-    obs_rms.update(raw)
+    ret_rms.update(np.zeros(n))                    # SB3 1.0 VecNormalize.reset: ret = 0, ret_rms.update(ret); obs_rms untouched
     want = np.clip((raw - obs_rms.mean) / np.sqrt(obs_rms.var + 1e-8), -10, 10)
     assert np.abs(o - want).max() < 1e-4
     for k in range(12):
@@ -622,6 +622,82 @@ def test_vecnormalize_matches_sb3_semantics():
     vn2.load_state_dict(sd)
     np.testing.assert_array_equal(vn2.obs_rms.var, vn.obs_rms.var)
     env.close()
+
+
+def test_statistics_are_bit_reproducible_and_stats_sync_every():
+    """the moments / Monitor statistics come from fixed-order sums (no atomics): two runs agree bit for bit, also across
+    CTA shapes; stats_sync_every=K merges the accumulated moments of K steps at once (same statistics up to rounding
+    at the merge steps, stale normalisation in between)."""
+    from drloco_b200.vec_env import B200VecNormalize
+    n, steps = 512, 12
+    g = torch.Generator(device="cuda")
+    g.manual_seed(3)
+    acts = torch.rand(steps, n, 8, device="cuda", generator=g) * 2 - 1
+    runs = []
+    for block, every in ((128, 1), (64, 1), (128, 4)):
+        env = _env(W3D, n, seed=21)
+        env.debug_set(block_threads=block)
+        vn = B200VecNormalize(env, stats_sync_every=every)
+        vn.reset_tensor()
+        outs = []
+        for k in range(steps):
+            o, r, d = vn.step_tensor(acts[k])
+            outs.append((o.clone(), r.clone()))
+        runs.append(dict(mean=vn.obs_rms.mean, var=vn.obs_rms.var, count=vn.obs_rms.count, rvar=vn.ret_rms.var,
+                         outs=outs, stats=env.stats()))
+        env.close()
+    a, b, c = runs
+    np.testing.assert_array_equal(a["mean"], b["mean"])
+    np.testing.assert_array_equal(a["var"], b["var"])
+    assert a["rvar"] == b["rvar"] and a["stats"] == b["stats"]
+    for (o1, r1), (o2, r2) in zip(a["outs"], b["outs"]):
+        assert torch.equal(o1, o2) and torch.equal(r1, r2)
+    # K = 4 over 12 steps: merged at steps 4, 8, 12 - the same data has been merged by the end
+    assert c["count"] == a["count"]
+    np.testing.assert_allclose(c["mean"], a["mean"], rtol=1e-12, atol=1e-14)
+    np.testing.assert_allclose(c["var"], a["var"], rtol=1e-10)
+    assert abs(c["rvar"] - a["rvar"]) <= 1e-10 * a["rvar"]
+    assert not torch.equal(c["outs"][1][0], a["outs"][1][0])          # steps 1-3 were normalised with stale statistics
+
+
+def test_reset_update_modes_seed_and_lazy_infos():
+    from drloco_b200.vec_env import B200VecNormalize, LazyInfos
+    n = 64
+    env = _env(W3D, n)
+    vn = B200VecNormalize(env, reset_update="obs")
+    o = vn.reset()
+    raw = env.obs.cpu().numpy().astype(np.float64)
+    from oracle.env_oracle import RunningMeanStd
+    rms = RunningMeanStd(shape=(env.obs_dim,))
+    rms.update(raw)
+    assert np.abs(o - np.clip((raw - rms.mean) / np.sqrt(rms.var + 1e-8), -10, 10)).max() < 1e-4
+    assert vn.ret_rms.count == pytest.approx(1e-4)                     # "obs" mode leaves the return statistics alone
+    # infos: list-like, fresh dict per entry, nothing shared between entries or steps
+    _, _, d, infos = vn.step(np.zeros((n, 8), np.float32))
+    assert isinstance(infos, LazyInfos) and len(infos) == n and infos[0] == {} and infos[0] is not infos[1]
+    infos[0]["x"] = 1
+    assert infos[0]["x"] == 1 and "x" not in infos[1]
+    _, _, _, infos2 = vn.step(np.zeros((n, 8), np.float32))
+    assert "x" not in infos2[0] and len(list(infos2)) == n
+    # seed(): re-keys the RSI stream (utils.py:113): envs built with different seeds draw the same initial states once
+    # they are given the same seed, and different ones otherwise
+    env2 = _env(W3D, n, seed=99)
+    assert env.seed(1234) == [1234 + i for i in range(n)] and env2.seed(1234)[0] == 1234
+    env.debug_set(frame_skip_override=0)
+    vn.reset()
+    env2.reset()
+    ca, cb = env.get_state()[2], env2.get_state()[2]
+    assert not np.array_equal(ca[:, :2], cb[:, :2])                     # reset counters differ (env was reset before)
+    env3 = _env(W3D, n, seed=7)
+    env3.seed(1234)
+    env3.reset()
+    np.testing.assert_array_equal(env3.get_state()[2][:, :2], cb[:, :2])
+    env3.seed(4321)
+    env3.reset()
+    env2.reset()
+    assert not np.array_equal(env3.get_state()[2][:, :2], env2.get_state()[2][:, :2])
+    for e in (env, env2, env3):
+        e.close()
 
 
 def test_vec_env_factory_save_load(tmp_path):

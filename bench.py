@@ -115,57 +115,98 @@ def fp32_peak_tflops(device_index: int) -> float:
 _WORKER = {}
 
 
-def _oracle_init(n_envs, seed_base):
-    """per-process initialiser: one OracleVecEnv per worker, kept across bench steps (like a SubprocVecEnv worker)."""
+def _reference_tree():
+    """baseline/_ref (copy of the reference's Python made by baseline/build_ref.py) or the container's checkout"""
+    for root in (os.path.join(REPO, "baseline", "_ref"), "/root/reference"):
+        if os.path.isdir(os.path.join(root, "drloco", "mujoco")):
+            return root
+    return None
+
+
+def _oracle_init(n_envs, seed_base, want_reference=True):
+    """per-process initialiser (like a SubprocVecEnv worker): the reference's own, unmodified
+    ``Monitor(MimicWalker3dEnv())`` Python (drloco/common/utils.py:109-125) imported from baseline/_ref over
+    oracle/liboracle.so when the copy exists, else the numpy restatement of the env logic (oracle/env_oracle.py)."""
     import random
 
     import numpy as np
-
-    from drloco_b200.walkers import make_spec
-    from oracle.env_oracle import OracleVecEnv
-    from oracle.physics import OraclePhysics
     seed = seed_base + os.getpid()
     random.seed(seed)
     np.random.seed(seed % (2 ** 31))
+    tree = _reference_tree() if want_reference else None
+    if tree is not None:
+        from baseline import ref_runner
+        ref_runner.use_reference_tree(tree)
+        Env, Monitor, _utils = ref_runner.load_reference()
+        envs = [Monitor(Env()) for _ in range(n_envs)]
+        for e in envs:
+            e.reset()
+        _WORKER.update(kind="reference", envs=envs, rng=np.random.default_rng(seed), n=n_envs, act=8,
+                       phys=ref_runner.PHYSICS_SECONDS)
+        return
+    from drloco_b200.walkers import make_spec
+    from oracle.env_oracle import OracleVecEnv
+    from oracle.physics import OraclePhysics
     spec = make_spec()
     venv = OracleVecEnv(spec, n_envs, lambda: OraclePhysics(spec.model))
     venv.reset()
-    _WORKER.update(venv=venv, rng=np.random.default_rng(seed), n=n_envs, act=spec.act_dim)
+    _WORKER.update(kind="port", venv=venv, rng=np.random.default_rng(seed), n=n_envs, act=spec.act_dim, phys=[0.0])
 
 
 def _oracle_run(n_steps):
-    """n_steps control steps of this worker's envs -> (env-steps, seconds)."""
+    """n_steps control steps of this worker's envs -> (env-steps, seconds, seconds inside the physics library, kind)."""
     import numpy as np
     w = _WORKER
+    p0 = w["phys"][0]
     t0 = time.perf_counter()
-    for _ in range(n_steps):
-        w["venv"].step(w["rng"].uniform(-1, 1, (w["n"], w["act"])).astype(np.float32))
-    return w["n"] * n_steps, time.perf_counter() - t0
+    if w["kind"] == "reference":
+        for _ in range(n_steps):                          # DummyVecEnv.step_wait semantics (SB3 1.0), written out
+            acts = w["rng"].uniform(-1, 1, (w["n"], w["act"])).astype(np.float32)
+            for e, a in zip(w["envs"], acts):
+                _obs, _rew, done, info = e.step(a)
+                if done:
+                    info["terminal_observation"] = _obs
+                    e.reset()
+    else:
+        for _ in range(n_steps):
+            w["venv"].step(w["rng"].uniform(-1, 1, (w["n"], w["act"])).astype(np.float32))
+    return w["n"] * n_steps, time.perf_counter() - t0, w["phys"][0] - p0, w["kind"]
 
 
 def _oracle_worker(args):
-    """env-steps/s of the CPU oracle stack in this process: (n_envs, n_steps, seed) -> (steps, seconds)."""
-    n_envs, n_steps, seed = args
-    _oracle_init(n_envs, seed)
+    """env-steps/s of the CPU stack in this process: (n_envs, n_steps, seed, want_reference) -> _oracle_run result"""
+    n_envs, n_steps, seed, want_reference = args
+    _oracle_init(n_envs, seed, want_reference)
     _oracle_run(5)
     return _oracle_run(n_steps)
 
 
+PHYSICS_LIB = "oracle/liboracle.so (float64 C restatement of the MuJoCo pipeline, oracle/walker_physics.c; MuJoCo itself is not installable here)"
+
+
 def cpu_baseline_single(budget_s: float = 12.0):
-    """bounded single-core sample of the oracle stack (kind = "port")."""
+    """bounded single-core sample of the CPU stack (rank 0, N = 1)."""
+    import multiprocessing as mp
+
     from oracle import physics
     physics.build()
-    steps, secs = _oracle_worker((8, 50, 0))
-    rate = steps / secs
-    n_steps = max(50, int(budget_s * rate / 8))
-    steps, secs = _oracle_worker((8, n_steps, 1))
-    return {"value": steps / secs, "unit": "env-steps/s", "cores": 1, "kind": "port",
-            "sample": f"8 envs x {n_steps} control steps, W3D RK4, random actions, numpy env logic + float64 C physics "
-                      f"(oracle/), {secs:.1f} s"}
+    ctx = mp.get_context("fork")
+    with ctx.Pool(1) as pool:                              # own process: the reference import chdir()s and stubs modules
+        steps, secs, _p, _k = pool.apply(_oracle_worker, ((8, 30, 0, True),))
+        rate = steps / secs
+        n_steps = max(30, int(budget_s * rate / 8))
+        steps, secs, phys, kind = pool.apply(_oracle_worker, ((8, n_steps, 1, True),))
+    logic = ("the reference's unmodified MimicWalker3dEnv + Monitor Python (baseline/_ref)" if kind == "reference"
+             else "numpy restatement of the reference env logic (oracle/env_oracle.py)")
+    return {"value": steps / secs, "unit": "env-steps/s", "cores": 1, "kind": kind,
+            "sample": f"8 envs x {n_steps} control steps, W3D RK4, random actions; {logic} over {PHYSICS_LIB}; "
+                      f"{secs:.1f} s, {100 * phys / secs:.0f}% of it inside the physics library"}
 
 
 def run_reference(args, emit):
-    """--impl reference: the reference path (SubprocVecEnv: one process per env) restated by the oracle on all cores."""
+    """--impl reference: the reference's path on the host cores - SubprocVecEnv = one process per env worker
+    (drloco/common/utils.py:109-125), each running the reference's own Monitor(MimicWalker3dEnv()) Python from
+    baseline/_ref over the physics restatement (falls back to the numpy port of the env logic when the copy is absent)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -177,7 +218,7 @@ def run_reference(args, emit):
     # size each step so that steps+warmup stay within a few minutes: one "step" = 40 control steps of all envs
     ctrl_per_step = 40
     ctx = mp.get_context("fork")
-    total_steps, t_total = 0, 0.0
+    total_steps, t_total, phys_total, busy_total, kind = 0, 0.0, 0.0, 0.0, "port"
     with ctx.Pool(cores, initializer=_oracle_init, initargs=(per_proc_envs, 1000)) as pool:
         t0 = time.perf_counter()
         for k in range(args.warmup):
@@ -189,11 +230,17 @@ def run_reference(args, emit):
         for k in range(args.steps):
             res = pool.map(_oracle_run, [ctrl_per_step] * cores, chunksize=1)
             total_steps += sum(r[0] for r in res)
+            busy_total += sum(r[1] for r in res)
+            phys_total += sum(r[2] for r in res)
+            kind = res[0][3]
         t_total = time.perf_counter() - t0
     value = total_steps / t_total
-    sample = (f"{cores} processes x {per_proc_envs} envs x {ctrl_per_step} control steps per bench step; oracle stack "
-              "(reference env logic restated in numpy + float64 C restatement of the MuJoCo pipeline); MuJoCo itself "
-              "is not installable here")
+    logic = ("the reference's unmodified MimicWalker3dEnv + Monitor Python (baseline/_ref, import stubs for gym / "
+             "mujoco_py / SB3)" if kind == "reference" else
+             "numpy restatement of the reference env logic (oracle/env_oracle.py; baseline/_ref absent)")
+    sample = (f"{cores} processes x {per_proc_envs} envs x {ctrl_per_step} control steps per bench step; {logic}; "
+              f"physics: {PHYSICS_LIB}; {100 * phys_total / max(busy_total, 1e-9):.0f}% of the workers' time inside the "
+              f"physics library, the rest Python glue")
     line = {"impl": "reference", "metric": "env-steps/s incl. DeepMimic reward", "value": value, "unit": "env-steps/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": t_total / max(1, args.steps) * 1e3, "higher_is_better": True, "scaling": "weak",
@@ -202,7 +249,8 @@ def run_reference(args, emit):
             "config": {"workload": W3D_WORKLOAD % args.envs_per_gpu, "envs_per_gpu": args.envs_per_gpu,
                        "integrator": "rk4", "frame_skip": 5, "parallelism": f"{cores} host processes (SubprocVecEnv-like)",
                        "sample_envs": cores * per_proc_envs},
-            "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": cores, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": cores, "kind": kind, "sample": sample,
+                             "physics_fraction": phys_total / max(busy_total, 1e-9)},
             "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     emit(line)

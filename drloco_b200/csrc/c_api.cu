@@ -17,6 +17,7 @@ namespace drl {
 size_t step_smem_bytes(int G, int envs_per_block, int fdv);
 cudaError_t launch_step(const StepArgs& a, int nv, int G, int rk4, int reset_only, int block, bool debug, int fdv,
                         cudaStream_t st);
+cudaError_t launch_running_rsi(const int* state_i, int* out, int n, cudaStream_t st);
 bool topology_matches(int nv, int nb, const int* body_parent, const int* dof_body, const int* dof_type);
 cudaError_t launch_extras(const float* state_f, const float* last, float* out, int n, int G, cudaStream_t st);
 cudaError_t launch_state_copy(float* state_f, int* state_i, int* state_as, float* qpos, float* qvel, int* cursor, int n,
@@ -568,6 +569,14 @@ extern "C" int drl_get_episode_positions(DrlEnv* e, int32_t* rsi_pos, int32_t* e
   if (rsi_pos) CUDA_TRY(cudaMemcpyAsync(rsi_pos, e->ring_rsi_pos, n * sizeof(int), cudaMemcpyDeviceToDevice, st));
   if (et_pos) CUDA_TRY(cudaMemcpyAsync(et_pos, e->ring_et_pos, n * sizeof(int), cudaMemcpyDeviceToDevice, st));
   if (difficult) CUDA_TRY(cudaMemcpyAsync(difficult, e->ring_difficult, n, cudaMemcpyDeviceToDevice, st));
+  return DRL_OK;
+}
+
+extern "C" int drl_get_running_rsi_positions(DrlEnv* e, int32_t* rsi_pos, void* stream) {
+  int rc = ready(e, "drl_get_running_rsi_positions");
+  if (rc) return rc;
+  if (!rsi_pos) return fail(DRL_ERR_INVALID, "drl_get_running_rsi_positions: null tensor");
+  CUDA_TRY(launch_running_rsi(e->state_i, rsi_pos, e->cfg.num_envs, (cudaStream_t)stream));
   return DRL_OK;
 }
 

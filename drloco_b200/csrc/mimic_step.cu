@@ -693,6 +693,15 @@ __global__ void extras_kernel(const float* __restrict__ state_f, const float* __
   out[i] = val;
 }
 
+// Monitor.rsi_positions of the RUNNING episodes (monitor_wrapper.py:91-93): refs._pos after the first step of the episode,
+// kept in the upper half of the cursor flags; -1 while the episode has not made its first step
+__global__ void running_rsi_kernel(const int* __restrict__ state_i, int* __restrict__ out, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int* si = state_i + (size_t)i * kCurCount8;
+  out[i] = si[kCurEpDur] > 0 ? (int)((unsigned)si[kCurFlags] >> 16) : -1;
+}
+
 // strided copies between the padded state rows and dense [N][nv] user tensors
 __global__ void state_copy_kernel(float* state_f, int* state_i, int* state_as, float* qpos, float* qvel, int* cursor,
                                   int n, int nv, int G, int to_state) {
@@ -802,6 +811,11 @@ bool topology_matches(int nv, int nb, const int* body_parent, const int* dof_bod
   if (nv == 14) return topo_ok<14>(nb, body_parent, dof_body, dof_type);
   if (nv == 19) return topo_ok<19>(nb, body_parent, dof_body, dof_type);
   return false;
+}
+
+cudaError_t launch_running_rsi(const int* state_i, int* out, int n, cudaStream_t st) {
+  running_rsi_kernel<<<(n + 255) / 256, 256, 0, st>>>(state_i, out, n);
+  return cudaGetLastError();
 }
 
 cudaError_t launch_extras(const float* state_f, const float* last, float* out, int n, int G, cudaStream_t st) {

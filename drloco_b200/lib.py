@@ -33,6 +33,7 @@ PROTOTYPES = {
     "drl_reset_stats": (C.c_int, [vp, vp]),
     "drl_get_episode_ring": (C.c_int, [vp, vp, vp, i32, C.POINTER(C.c_int64), vp]),
     "drl_get_episode_positions": (C.c_int, [vp, vp, vp, vp, i32, vp]),
+    "drl_get_running_rsi_positions": (C.c_int, [vp, vp, vp]),
     "drl_set_eval_mode": (C.c_int, [vp, i32]),
     "drl_set_det_init_counters": (C.c_int, [vp, vp]),
     "drl_set_speed_profile": (C.c_int, [vp, vp, i32]),

@@ -5,6 +5,11 @@ hyper-parameters (``drloco/config/hypers.py:68-116``) and network (``drloco/cust
 layers *shared* between policy and value head — Q15 —, state-independent log-std initialised at -0.75), on device
 tensors end to end: observations, actions, rewards and the rollout buffer never leave HBM; the environment is stepped
 through ``B200VecNormalize.step_tensor``.  The MLP uses plain PyTorch (cuBLAS GEMMs): it is not part of the hot path.
+
+Data parallel over the GPUs of a node (one process per GPU, ``torch.distributed``): every rank rolls out its own shard
+of the environments (no exchange inside ``step`` beyond the VecNormalize statistics), the learner replicas start from
+rank 0's parameters and all-reduce ONE flat gradient bucket per minibatch (the parameter gradients are views of it), so
+that the replicas stay bit-identical; episode statistics are all-reduced at the logging cadence.
 """
 from __future__ import annotations
 
@@ -69,15 +74,35 @@ class ActorCritic(nn.Module):
 class PPO:
     """On-policy loop: collect n_steps x N transitions on the device, GAE(lambda), clipped surrogate updates."""
 
-    def __init__(self, env, cfg: Optional[PPOConfig] = None, seed: int = 0):
+    def __init__(self, env, cfg: Optional[PPOConfig] = None, seed: int = 0, distributed: Optional[bool] = None):
         self.env, self.cfg = env, cfg or PPOConfig()
         self.device = env.device
+        dist = torch.distributed
+        if distributed is None:
+            distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+        self.distributed = bool(distributed)
+        self.world = dist.get_world_size() if self.distributed else 1
+        self.rank = dist.get_rank() if self.distributed else 0
         torch.manual_seed(seed)
         venv = env.venv if hasattr(env, "venv") else env
         self.N, self.D, self.A = venv.num_envs, venv.obs_dim, venv.act_dim
         self.n_steps = max(1, self.cfg.batch_size // self.N)          # train.py:112
         self.policy = ActorCritic(self.D, self.A, self.cfg.hidden, self.cfg.init_logstd).to(self.device)
+        # one flat gradient bucket: every parameter's .grad is a view of it (a single all-reduce per minibatch)
+        params = list(self.policy.parameters())
+        self._gradbuf = torch.zeros(sum(p.numel() for p in params), device=self.device)
+        off = 0
+        for p in params:
+            p.grad = self._gradbuf[off:off + p.numel()].view_as(p)
+            off += p.numel()
+        if self.distributed:                                  # replicas start from rank 0's parameters
+            for p in params:
+                dist.broadcast(p.data, src=0)
+        torch.manual_seed(seed + 7919 * self.rank)            # exploration noise differs between the ranks
         self.opt = torch.optim.Adam(self.policy.parameters(), lr=self.cfg.lr_start, eps=1e-5)
+        # minibatch permutations: the same seed on every rank (each rank permutes its own shard identically)
+        self._perm_gen = torch.Generator(device=self.device)
+        self._perm_gen.manual_seed(1_000_003 + seed)
         self.num_timesteps = 0
         self.step_callback: Optional[Callable[[], object]] = None    # e.g. TrainingMonitor.on_step
         self.log: List[dict] = []
@@ -129,7 +154,7 @@ class PPO:
             delta = b["rew"][t] + self.cfg.gamma * nv * nonterminal - b["val"][t]
             last = delta + self.cfg.gamma * self.cfg.gae_lambda * nonterminal * last
             adv[t] = last
-        self.num_timesteps += self.n_steps * self.N
+        self.num_timesteps += self.n_steps * self.N * self.world      # global count: every rank collects its shard
         return obs, adv, adv + b["val"]
 
     def update(self, adv, ret):
@@ -141,7 +166,7 @@ class PPO:
         n = obs.shape[0]
         stats = []
         for _ in range(cfg.n_epochs):
-            perm = torch.randperm(n, device=self.device)
+            perm = torch.randperm(n, device=self.device, generator=self._perm_gen)
             for s in range(0, n, cfg.minibatch_size):
                 idx = perm[s:s + cfg.minibatch_size]
                 mean, val = self.policy(obs[idx])
@@ -155,8 +180,11 @@ class PPO:
                 vl = ((ret[idx] - vclip) ** 2).mean()
                 ent = d.entropy().sum(-1).mean()
                 loss = pl + cfg.vf_coef * vl - cfg.ent_coef * ent
-                self.opt.zero_grad(set_to_none=True)
+                self._gradbuf.zero_()                                 # grads are views of the bucket: keep them
                 loss.backward()
+                if self.distributed:                                  # mean gradient over the ranks' shards
+                    torch.distributed.all_reduce(self._gradbuf, op=torch.distributed.ReduceOp.SUM)
+                    self._gradbuf /= self.world
                 nn.utils.clip_grad_norm_(self.policy.parameters(), cfg.max_grad_norm)
                 self.opt.step()
                 stats.append((pl.detach(), vl.detach(), ent.detach()))
@@ -175,11 +203,9 @@ class PPO:
             pl, vl, ent = self.update(adv, ret)
             it += 1
             if it % log_every == 0 or self.num_timesteps >= total:
-                st = venv.stats()
-                venv.reset_stats()
+                st = self._global_stats(venv)
                 row = dict(steps=self.num_timesteps, wall_s=time.time() - t0,
-                           mean_step_reward=(self.env.get_original_reward().mean().item()
-                                             if hasattr(self.env, "get_original_reward") else float("nan")),
+                           mean_step_reward=self._global_mean_reward(),
                            mean_ep_len=st["ep_len_sum"] / max(1.0, st["episodes"]),
                            mean_ep_ret=st["ep_ret_sum"] / max(1.0, st["episodes"]),
                            moved_distance=st["moved_distance_sum"] / max(1.0, st["episodes"]),
@@ -190,6 +216,32 @@ class PPO:
                 if callback:
                     callback(self, row)
         return self
+
+
+    def _global_stats(self, venv) -> dict:
+        """episode statistics since the last call, summed over the ranks (logging cadence)"""
+        st = venv.stats()
+        if self.distributed:
+            keys = sorted(st)
+            t = torch.tensor([float(st[k]) for k in keys], dtype=torch.float64, device=self.device)
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.SUM)
+            st = dict(zip(keys, t.cpu().tolist()))
+        venv.reset_stats()
+        return st
+
+    def _global_mean_reward(self) -> float:
+        if not hasattr(self.env, "get_original_reward"):
+            return float("nan")
+        m = self.env.get_original_reward().mean().reshape(1).clone()
+        if self.distributed:
+            torch.distributed.all_reduce(m, op=torch.distributed.ReduceOp.SUM)
+            m /= self.world
+        return m.item()
+
+    def parameter_checksum(self) -> torch.Tensor:
+        """float64 (sum, sum of squares) over all parameters: equal on every rank iff the replicas are in lockstep"""
+        v = torch.cat([p.detach().reshape(-1) for p in self.policy.parameters()]).double()
+        return torch.stack([v.sum(), (v * v).sum()])
 
 
 @torch.no_grad()

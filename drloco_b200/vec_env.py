@@ -168,6 +168,7 @@ class B200MimicVecEnv:
         self._ep_lens_base = 0        # set_attr('ep_lens', []) marks the ring position (callback.py:69-70)
         self._closed = False
         self.launches = 0             # kernels launched through this env (bench: gpu_launches)
+        self._config_epoch = 0        # bumped by every setter that changes what drl_step enqueues (captured graphs)
 
     # ------------------------------------------------------------------ construction helpers
     def _make_config(self, seed, env_id_offset, lanes_per_env) -> cabi.DrlConfig:
@@ -378,12 +379,22 @@ class B200MimicVecEnv:
             # the reference returns one list per env and the callback flattens them (callback.py:227-230)
             lens = self.episode_lengths().tolist()
             return [lens] + [[] for _ in idx[1:]]
-        if attr_name in ("et_positions", "difficult_rsi_phases"):
-            # as ep_lens: one merged list (env 0), finished episodes only.  Monitor.rsi_positions also holds the entry of
-            # each env's running episode; those are not in the ring (episode_records() documents the finished ones).
+        if attr_name in ("et_positions", "difficult_rsi_phases", "rsi_positions"):
+            # as ep_lens: one merged list (env 0).  rsi_positions = the finished episodes of the ring followed by the
+            # entries of the episodes still running (Monitor appends on an episode's first step, monitor_wrapper.py:91-93)
             rec = self.episode_records()
-            vals = rec["et_pos"] if attr_name == "et_positions" else rec["rsi_pos"][rec["difficult"]]
-            return [vals.tolist()] + [[] for _ in idx[1:]]
+            if attr_name == "et_positions":
+                vals = rec["et_pos"].tolist()
+            elif attr_name == "difficult_rsi_phases":
+                vals = rec["rsi_pos"][rec["difficult"]].tolist()
+            else:
+                with torch.cuda.device(self.device):
+                    run = torch.zeros(self.num_envs, dtype=torch.int32, device=self.device)
+                    lib.check(self._lib.drl_get_running_rsi_positions(self._handle, _ptr(run), self._stream()),
+                              "drl_get_running_rsi_positions")
+                run = run.cpu().numpy()
+                vals = rec["rsi_pos"].tolist() + run[run >= 0].tolist()
+            return [vals] + [[] for _ in idx[1:]]
         if attr_name in ("num_envs", "obs_dim", "act_dim"):
             return [getattr(self, attr_name)] * len(idx)
         if attr_name in ("ep_dur", "i_step", "pos"):
@@ -403,6 +414,7 @@ class B200MimicVecEnv:
 
     def env_method(self, method_name: str, *args, indices=None, **kwargs) -> List[Any]:
         idx = self._indices(indices)
+        self._config_epoch += 1
         if method_name == "activate_evaluation":             # mimic_env.py:245
             lib.check(self._lib.drl_set_eval_mode(self._handle, 1), "drl_set_eval_mode")
             return [None] * len(idx)
@@ -422,6 +434,7 @@ class B200MimicVecEnv:
         reference's own `_get_obs` then unpacks the scalar profile value with `*` and raises TypeError (run.py:76-79 is
         its only caller and is off by default, Q26); the evident intent - obs[des_vel] = profile value - is what runs
         here.  An empty ``speeds`` switches speed control off (not in the reference)."""
+        self._config_epoch += 1
         prof = speed_profile(speeds, speed_profile_duration, self.cfg.ctrl_freq) if len(speeds) else \
             np.zeros(0, np.float32)
         self.desired_walking_speed_trajectory = prof
@@ -433,6 +446,7 @@ class B200MimicVecEnv:
     def set_playback(self, on: bool = True) -> None:
         """kinematic playback mode (mimic_env.py:265-293): `step` skips the physics and sets qpos/qvel from the mocap
         after `refs.next()`; observation, reward, termination and Monitor logic run as usual."""
+        self._config_epoch += 1
         lib.check(self._lib.drl_set_playback(self._handle, int(bool(on))), "drl_set_playback")
 
     def playback_ref_trajectories(self, timesteps: int = 2000):
@@ -488,6 +502,7 @@ class B200MimicVecEnv:
         return dict(zip(("lanes_per_env", "block_threads", "grid_blocks", "smem_bytes"), [v.value for v in vals]))
 
     def debug_set(self, frame_skip_override=-1, block_threads=0, enable_dump=False):
+        self._config_epoch += 1
         lib.check(self._lib.drl_debug_set(self._handle, frame_skip_override, block_threads, int(enable_dump)),
                   "drl_debug_set")
 
@@ -643,10 +658,18 @@ class B200VecNormalize:
         upd_obs = self.training if upd_obs is None else upd_obs
         upd_ret = (self.training and rew is not None) if upd_ret is None else upd_ret
         K = self.stats_sync_every
-        ready = torch.cuda.Event()
-        ready.record(main)
-        with torch.cuda.device(self.device), torch.cuda.stream(self._side):
-            self._side.wait_event(ready)
+        # wait=True: the kernel simply follows the env step on the caller's stream.  wait=False: it goes to the side
+        # stream behind an event, so that the caller's next env step can overlap it.
+        stream = main if wait else self._side
+        if wait:
+            if self._ev_used[k ^ 1]:                     # the previous call ran on the side stream: order after it
+                main.wait_event(self._done_ev[k ^ 1])
+        else:
+            ready = torch.cuda.Event()
+            ready.record(main)
+        with torch.cuda.device(self.device), torch.cuda.stream(stream):
+            if not wait:
+                self._side.wait_event(ready)
             sync_every = K
             if self.exchange == "nccl" and (upd_obs or upd_ret):
                 # host-issued collective: the kernel then sees a single-rank exchange of already reduced moments
@@ -671,14 +694,15 @@ class B200VecNormalize:
                                                  self.num_envs, self._D, _ptr(packed), _ptr(src), _ptr(dst),
                                                  _ptr(self.ret), _ptr(done), float(self.clip_obs),
                                                  float(self.clip_reward), float(self.epsilon), flags, self._comm,
-                                                 int(sync_every), self.venv._stream()), "drl_vecnorm_step")
+                                                 int(sync_every), C.c_void_p(stream.cuda_stream)), "drl_vecnorm_step")
             self.launches += 1
             self._calls += 1
             self._cur = 1 - self._cur
-            self._done_ev[k].record(self._side)
-            self._ev_used[k] = True
-        if wait:
-            main.wait_event(self._done_ev[k])
+            if not wait:
+                self._done_ev[k].record(self._side)
+                self._ev_used[k] = True
+            else:
+                self._ev_used[k] = False
 
     def _guard_reuse(self):
         """before the env overwrites the output set it used two steps ago, make sure that step's normalisation is done."""
@@ -752,9 +776,13 @@ class B200VecNormalize:
         o = self._h_np["obs"][self._hk]
         return o.copy() if self.copy_outputs else o
 
-    def step_async(self, actions, inject=None):
-        h = self._host_buffers()
-        self._h_np["act"][...] = np.asarray(actions, np.float32).reshape(self.num_envs, -1)
+    # The device side of a numpy-API step (H2D of the actions, env step, statistics kernel, terminal-row compaction and
+    # the D2H copies) is captured into CUDA graphs, one per combination of the alternating buffer sets, and replayed
+    # with a single launch.  `use_graph = False` (or an injected RSI draw, or the NCCL exchange) takes the eager path.
+    use_graph = True
+
+    def _enqueue_step(self, inject=None):
+        h = self._h
         self._d_act.copy_(h["act"], non_blocking=True)
         obs, rew, done = self.step_tensor(self._d_act, inject)
         self._hk ^= 1
@@ -767,13 +795,67 @@ class B200VecNormalize:
                                 self.epsilon, self.norm_obs, self.venv._stream())
         self.launches += 1
 
+    def _graph_key(self):
+        v = self.venv
+        return (v._cur, self._k, self._cur, self._hk, bool(self.training), bool(self.norm_obs), bool(self.norm_reward),
+                float(self.clip_obs), float(self.clip_reward), v._config_epoch, self._calls % self.stats_sync_every)
+
+    def step_async(self, actions, inject=None):
+        self._host_buffers()
+        self._h_np["act"][...] = np.asarray(actions, np.float32).reshape(self.num_envs, -1)
+        if not self.use_graph or inject is not None or self.exchange == "nccl":
+            return self._enqueue_step(inject)
+        if not hasattr(self, "_graphs"):
+            self._graphs, self._graph_warm = {}, 0
+        if self._graph_warm < 2:                          # library one-time setup (function attributes) stays out of a capture
+            self._graph_warm += 1
+            return self._enqueue_step(None)
+        key = self._graph_key()
+        entry = self._graphs.get(key)
+        v = self.venv
+        if entry is None:
+            # quiesce, then capture this step's enqueue sequence (it also executes nothing: replay right after)
+            torch.cuda.synchronize(self.device)
+            self._ev_used = [False, False]
+            before = (v._cur, self._k, self._cur, self._hk, self._calls, v.launches, self.launches)
+            g = torch.cuda.CUDAGraph()
+            try:
+                with torch.cuda.graph(g, stream=self._capture_stream()):
+                    self._enqueue_step(None)
+            except Exception:
+                # capture is an optimisation: fall back to the eager path for good
+                (v._cur, self._k, self._cur, self._hk, self._calls, v.launches, self.launches) = before
+                self.use_graph = False
+                torch.cuda.synchronize(self.device)
+                return self._enqueue_step(None)
+            after = (v._cur, self._k, self._cur, self._hk)
+            dl = (v.launches - before[5], self.launches - before[6])
+            (v._cur, self._k, self._cur, self._hk, self._calls, v.launches, self.launches) = before
+            entry = self._graphs[key] = (g, after, dl)
+        g, after, dl = entry
+        g.replay()
+        v._cur, self._k, self._cur, self._hk = after
+        self._calls += 1
+        v.launches += dl[0]
+        self.launches += dl[1]
+        self._ev_used = [False, False]
+
+    def _capture_stream(self):
+        if not hasattr(self, "_cap_stream"):
+            with torch.cuda.device(self.device):
+                self._cap_stream = torch.cuda.Stream(device=self.device)
+        return self._cap_stream
+
     def step_wait(self):
         hn = self._h_np
         torch.cuda.current_stream(self.device).synchronize()
         done = hn["done"].astype(bool)
         infos = LazyInfos(self.num_envs, self._trows.collect(np.float32))
-        obs = hn["obs"][self._hk]
-        return (obs.copy() if self.copy_outputs else obs), hn["rew"].copy(), done, infos
+        if self.copy_outputs:
+            obs = self._h["obs"][self._hk].clone().numpy()          # multi-threaded copy out of the pinned buffer
+        else:
+            obs = hn["obs"][self._hk]
+        return obs, hn["rew"].copy(), done, infos
 
     def step(self, actions, inject=None):
         self.step_async(actions, inject)

@@ -110,7 +110,8 @@ typedef struct {
   float mirror_obs_sign[DRL_MAX_OBS];
   int32_t mirror_act_idx[DRL_MAX_ACT];
   float mirror_act_sign[DRL_MAX_ACT];
-  int32_t lanes_per_env;         /* 0 = choose from num_envs; else 16 or 32 */
+  int32_t lanes_per_env;         /* lanes per environment; fixed by the model: 16 for nv <= 16 (walker3d), 32 otherwise.
+                                  * 0 = that value; anything else must equal it (drl_upload_model rejects a mismatch) */
   int32_t early_termination;     /* MimicEnv.do_terminate_early (mimic_env.py:652-702).  The reference defines the check
                                   * but never lets it end an episode (mimic_env.py:120-123): 0 = same here, the three
                                   * reasons are only counted (DRL_STAT_ET_*); 1 = a firing check also sets done (the
@@ -205,6 +206,11 @@ int drl_get_episode_ring(DrlEnv* env, int32_t* ep_len, float* ep_ret, int32_t ca
  * device int32 / int32 / uint8 [capacity], each nullable. */
 int drl_get_episode_positions(DrlEnv* env, int32_t* rsi_pos, int32_t* et_pos, uint8_t* difficult, int32_t capacity,
                               void* stream);
+
+/* Monitor.rsi_positions also lists the episodes still running (the entry is appended on an episode's first step,
+ * monitor_wrapper.py:91-93): rsi_pos device int32 [N] = refs._pos after the first step of env i's current episode, or
+ * -1 while that episode has not stepped yet. */
+int drl_get_running_rsi_positions(DrlEnv* env, int32_t* rsi_pos, void* stream);
 
 /* MimicEnv.activate_evaluation (mimic_env.py:245): deterministic init states (straight_walk_trajecs.py:237-265) */
 int drl_set_eval_mode(DrlEnv* env, int32_t on);

@@ -24,7 +24,12 @@ def test_reference_arm_line():
     assert d["value"] > 100 and d["steps"] == 2 and d["gpu_launches"] == 0
     assert "BASELINE.json configs[1]" in d["config"]["workload"] and d["config"]["envs_per_gpu"] == 4096
     cb = d["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
+    # "reference": the reference's own Python (baseline/_ref, made by baseline/build_ref.py) ran; "port": the numpy
+    # restatement stood in because the copy is absent.  Either way the sample names the library that did the physics.
+    have_ref = os.path.isdir(os.path.join(ROOT, "baseline", "_ref", "drloco")) or os.path.isdir("/root/reference/drloco")
+    assert cb["kind"] == ("reference" if have_ref else "port")
+    assert cb["cores"] >= 1 and cb["value"] == d["value"] and "liboracle.so" in cb["sample"]
+    assert 0.0 < cb["physics_fraction"] < 1.0
     assert d["e2e"] == {"value": d["value"], "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
 
 

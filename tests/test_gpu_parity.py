@@ -337,6 +337,8 @@ def test_env_logic_and_monitor_on_injected_states():
     assert got == sorted(want)
     assert sorted(env.get_attr("et_positions")[0]) == sorted(x for m in ora.envs for x in m.et_positions)
     assert sorted(env.get_attr("difficult_rsi_phases")[0]) == sorted(x for m in ora.envs for x in m.difficult_rsi_phases)
+    # rsi_positions also lists the episodes still running (monitor_wrapper.py:91-93)
+    assert sorted(env.get_attr("rsi_positions")[0]) == sorted(x for m in ora.envs for x in m.rsi_positions)
     assert rec["difficult"].sum() >= 1
     st = env.stats()
     assert st["episodes"] == n_done and st["falls"] + st["timeouts"] == n_done and st["timeouts"] >= 3
@@ -625,16 +627,17 @@ def test_vecnormalize_matches_sb3_semantics():
 
 
 def test_statistics_are_bit_reproducible_and_stats_sync_every():
-    """the moments / Monitor statistics come from fixed-order sums (no atomics): two runs agree bit for bit, also across
-    CTA shapes; stats_sync_every=K merges the accumulated moments of K steps at once (same statistics up to rounding
-    at the merge steps, stale normalisation in between)."""
+    """the moments / Monitor statistics come from fixed-order sums (no atomics): two runs of the same launch
+    configuration agree bit for bit (another CTA shape groups the additions differently: same to rounding);
+    stats_sync_every=K merges the accumulated moments of K steps at once (same statistics up to rounding at the merge
+    steps, stale normalisation in between)."""
     from drloco_b200.vec_env import B200VecNormalize
     n, steps = 512, 12
     g = torch.Generator(device="cuda")
     g.manual_seed(3)
     acts = torch.rand(steps, n, 8, device="cuda", generator=g) * 2 - 1
     runs = []
-    for block, every in ((128, 1), (64, 1), (128, 4)):
+    for block, every in ((128, 1), (128, 1), (64, 1), (128, 4)):
         env = _env(W3D, n, seed=21)
         env.debug_set(block_threads=block)
         vn = B200VecNormalize(env, stats_sync_every=every)
@@ -646,12 +649,15 @@ def test_statistics_are_bit_reproducible_and_stats_sync_every():
         runs.append(dict(mean=vn.obs_rms.mean, var=vn.obs_rms.var, count=vn.obs_rms.count, rvar=vn.ret_rms.var,
                          outs=outs, stats=env.stats()))
         env.close()
-    a, b, c = runs
-    np.testing.assert_array_equal(a["mean"], b["mean"])
-    np.testing.assert_array_equal(a["var"], b["var"])
-    assert a["rvar"] == b["rvar"] and a["stats"] == b["stats"]
-    for (o1, r1), (o2, r2) in zip(a["outs"], b["outs"]):
+    a, a2, b, c = runs
+    np.testing.assert_array_equal(a["mean"], a2["mean"])
+    np.testing.assert_array_equal(a["var"], a2["var"])
+    assert a["rvar"] == a2["rvar"] and a["stats"] == a2["stats"]
+    for (o1, r1), (o2, r2) in zip(a["outs"], a2["outs"]):
         assert torch.equal(o1, o2) and torch.equal(r1, r2)
+    np.testing.assert_allclose(b["mean"], a["mean"], rtol=1e-12, atol=1e-15)      # other CTA shape: other grouping
+    np.testing.assert_allclose(b["var"], a["var"], rtol=1e-10)
+    assert b["stats"]["episodes"] == a["stats"]["episodes"] and b["stats"]["env_steps"] == n * steps
     # K = 4 over 12 steps: merged at steps 4, 8, 12 - the same data has been merged by the end
     assert c["count"] == a["count"]
     np.testing.assert_allclose(c["mean"], a["mean"], rtol=1e-12, atol=1e-14)

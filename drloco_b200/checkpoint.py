@@ -78,8 +78,9 @@ def save_sb3_zip(path: str, policy, optimizer: Optional[torch.optim.Optimizer] =
     with zipfile.ZipFile(path, "w") as z:
         z.writestr("data", json.dumps(data or {}))
         z.writestr("policy.pth", blob(policy_to_sb3_state_dict(policy)))
-        if optimizer is not None:
-            z.writestr("policy.optimizer.pth", blob(optimizer.state_dict()))
+        # SB3's set_parameters(exact_match=True) expects the optimiser entry: always present (empty state when none given)
+        z.writestr("policy.optimizer.pth", blob(optimizer.state_dict() if optimizer is not None
+                                                else {"state": {}, "param_groups": []}))
         z.writestr("_stable_baselines3_version", SB3_VERSION)
 
 
@@ -110,10 +111,29 @@ class _Bag:
                     self.__dict__.update(part)
 
 
+# what a pickled VecNormalize legitimately needs besides the SB3 / gym classes (which are replaced by _Bag): numpy's
+# array reconstruction helpers and a handful of plain containers.  Nothing callable with side effects (eval, exec,
+# os.system, ...) can be reached through find_class.
+_SAFE_GLOBALS = {
+    ("numpy.core.multiarray", "_reconstruct"), ("numpy._core.multiarray", "_reconstruct"),
+    ("numpy.core.multiarray", "scalar"), ("numpy._core.multiarray", "scalar"),
+    ("numpy", "ndarray"), ("numpy", "dtype"), ("numpy", "float64"), ("numpy", "float32"), ("numpy", "int64"),
+    ("numpy", "bool_"), ("numpy.core.numeric", "_frombuffer"), ("numpy._core.numeric", "_frombuffer"),
+    ("collections", "OrderedDict"), ("collections", "deque"), ("copyreg", "_reconstructor"),
+    ("_codecs", "encode"),
+    ("builtins", "object"), ("builtins", "dict"), ("builtins", "list"), ("builtins", "tuple"), ("builtins", "set"),
+    ("builtins", "frozenset"), ("builtins", "int"), ("builtins", "float"), ("builtins", "bool"), ("builtins", "str"),
+    ("builtins", "bytes"), ("builtins", "bytearray"), ("builtins", "complex"), ("builtins", "slice"),
+}
+
+
 class _TolerantUnpickler(pickle.Unpickler):
     def find_class(self, module, name):
-        if module.split(".")[0] in ("numpy", "builtins", "collections", "copyreg", "_codecs"):
+        if (module, name) in _SAFE_GLOBALS:
             return super().find_class(module, name)
+        root = module.split(".")[0]
+        if root in ("builtins", "os", "posix", "nt", "subprocess", "sys", "importlib", "shutil", "socket"):
+            raise pickle.UnpicklingError(f"refusing to load {module}.{name} from an env file")
         return type(name, (_Bag,), {"__module__": module})
 
 

@@ -42,6 +42,19 @@ static int fail(int code, const char* fmt, ...) {
     if (e__ != cudaSuccess) return fail(DRL_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(e__)); \
   } while (0)
 
+// Every entry point runs on the env's device and leaves the caller's current device as it found it (several envs on
+// different GPUs may live in one process; PyTorch's current device must not change under the caller).
+struct DeviceGuard {
+  int prev = -1, dev;
+  explicit DeviceGuard(int d) : dev(d) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != dev) cudaSetDevice(dev);
+  }
+  ~DeviceGuard() {
+    if (prev >= 0 && prev != dev) cudaSetDevice(prev);
+  }
+};
+
 struct DrlEnv {
   DrlConfig cfg;
   DevModel hm;                 // host copy
@@ -102,18 +115,18 @@ extern "C" int drl_create(const DrlConfig* cfg, DrlEnv** out) {
   int ndev = 0;
   CUDA_TRY(cudaGetDeviceCount(&ndev));
   if (cfg->device < 0 || cfg->device >= ndev) return fail(DRL_ERR_INVALID, "drl_create: no CUDA device %d", cfg->device);
-  CUDA_TRY(cudaSetDevice(cfg->device));
   DrlEnv* e = new DrlEnv();
   e->cfg = *cfg;
   e->fd_version = env_int("DRLOCO_B200_FD", 2) == 1 ? 1 : 2;
-  e->stage_barrier = env_int("DRLOCO_B200_STAGE_BARRIER", 1) ? 1 : 0;
+  e->stage_barrier = env_int("DRLOCO_B200_STAGE_BARRIER", 1);      // 0 none, 1 start of evaluation, 2 before the solver
+  if (e->stage_barrier < 0 || e->stage_barrier > 2) e->stage_barrier = 1;
   *out = e;
   return DRL_OK;
 }
 
 extern "C" int drl_destroy(DrlEnv* e) {
   if (!e) return DRL_OK;
-  cudaSetDevice(e->cfg.device);
+  DeviceGuard guard__(e->cfg.device);
   void* ptrs[] = {e->d_model, e->state_f, e->state_i, e->state_as, e->state_d, e->extras_last, e->stats, e->ref, e->step_vel,
                   e->step_last_comx, e->des_vel_prefix, e->step_off, e->step_len, e->left_step, e->ring_len,
                   e->ring_ret, e->ring_head, e->debug, e->speed_profile, e->ring_rsi_pos, e->ring_et_pos, e->ring_difficult,
@@ -367,11 +380,11 @@ extern "C" int drl_upload_model(DrlEnv* e, const DrlWalkerModel* m) {
   e->nv = m->nv;
   e->G = G;
   e->block = 128;
+  DeviceGuard guard__(c.device);
   {
     const int b = env_int("DRLOCO_B200_BLOCK", 0);     // developer hook: CTA size of the step kernel
     if (b == 32 || b == 64 || b == 96 || b == 128) e->block = b;
   }
-  CUDA_TRY(cudaSetDevice(c.device));
   const size_t N = (size_t)c.num_envs;
   if (!e->d_model) {
     const int rc = alloc_state(e, N);
@@ -412,7 +425,7 @@ extern "C" int drl_upload_mocap(DrlEnv* e, int32_t cursor_mode, int32_t incremen
     if (step_off[i] < 0 || step_len[i] <= 2 * increment || step_off[i] + step_len[i] > n_samples)
       return fail(DRL_ERR_INVALID, "drl_upload_mocap: step %d out of range or shorter than two increments", i);
   }
-  CUDA_TRY(cudaSetDevice(e->cfg.device));
+  DeviceGuard guard__(e->cfg.device);
   const int G = e->G, nv = e->nv;
   std::vector<float> padded((size_t)n_samples * 2 * G, 0.f);
   for (int t = 0; t < n_samples; t++)
@@ -440,8 +453,6 @@ extern "C" int drl_upload_mocap(DrlEnv* e, int32_t cursor_mode, int32_t incremen
 static int ready(DrlEnv* e, const char* who) {
   if (!e) return fail(DRL_ERR_INVALID, "%s: null env", who);
   if (!e->have_model || !e->have_mocap) return fail(DRL_ERR_STATE, "%s: model and mocap must be uploaded first", who);
-  cudaError_t err = cudaSetDevice(e->cfg.device);
-  if (err != cudaSuccess) return fail(DRL_ERR_CUDA, "%s: %s", who, cudaGetErrorString(err));
   return DRL_OK;
 }
 
@@ -472,6 +483,7 @@ extern "C" int drl_reset(DrlEnv* e, const uint8_t* mask, const int32_t* inj_iste
                          void* stream) {
   int rc = ready(e, "drl_reset");
   if (rc) return rc;
+  DeviceGuard guard__(e->cfg.device);
   if (!obs) return fail(DRL_ERR_INVALID, "drl_reset: obs is null");
   StepArgs a = make_args(e);
   a.reset_mask = mask; a.inj_istep = inj_istep; a.inj_pos = inj_pos; a.obs = obs;
@@ -484,6 +496,7 @@ extern "C" int drl_step(DrlEnv* e, const float* actions, float* obs, float* rew,
                         const int32_t* inj_istep, const int32_t* inj_pos, void* stream) {
   int rc = ready(e, "drl_step");
   if (rc) return rc;
+  DeviceGuard guard__(e->cfg.device);
   if (!actions || !obs || !rew || !done) return fail(DRL_ERR_INVALID, "drl_step: null tensor");
   StepArgs a = make_args(e);
   a.actions = actions; a.obs = obs; a.rew = rew; a.done = done; a.terminal_obs = terminal_obs;
@@ -506,6 +519,7 @@ extern "C" int drl_attach_vecnorm(DrlEnv* e, float* ret, float gamma, double* pa
 extern "C" int drl_get_state(DrlEnv* e, float* qpos, float* qvel, int32_t* cursor, void* stream) {
   int rc = ready(e, "drl_get_state");
   if (rc) return rc;
+  DeviceGuard guard__(e->cfg.device);
   CUDA_TRY(launch_state_copy(e->state_f, e->state_i, e->state_as, qpos, qvel, cursor, e->cfg.num_envs, e->nv, e->G, 0,
                              (cudaStream_t)stream));
   return DRL_OK;
@@ -514,6 +528,7 @@ extern "C" int drl_get_state(DrlEnv* e, float* qpos, float* qvel, int32_t* curso
 extern "C" int drl_set_state(DrlEnv* e, const float* qpos, const float* qvel, const int32_t* cursor, void* stream) {
   int rc = ready(e, "drl_set_state");
   if (rc) return rc;
+  DeviceGuard guard__(e->cfg.device);
   CUDA_TRY(launch_state_copy(e->state_f, e->state_i, e->state_as, const_cast<float*>(qpos), const_cast<float*>(qvel),
                              const_cast<int32_t*>(cursor), e->cfg.num_envs, e->nv, e->G, 1, (cudaStream_t)stream));
   return DRL_OK;
@@ -522,6 +537,7 @@ extern "C" int drl_set_state(DrlEnv* e, const float* qpos, const float* qvel, co
 extern "C" int drl_get_extras(DrlEnv* e, float* extras, void* stream) {
   int rc = ready(e, "drl_get_extras");
   if (rc) return rc;
+  DeviceGuard guard__(e->cfg.device);
   if (!extras) return fail(DRL_ERR_INVALID, "drl_get_extras: null tensor");
   CUDA_TRY(launch_extras(e->state_f, e->extras_last, extras, e->cfg.num_envs, e->G, (cudaStream_t)stream));
   return DRL_OK;
@@ -530,6 +546,7 @@ extern "C" int drl_get_extras(DrlEnv* e, float* extras, void* stream) {
 extern "C" int drl_get_stats(DrlEnv* e, double* stats, void* stream) {
   int rc = ready(e, "drl_get_stats");
   if (rc) return rc;
+  DeviceGuard guard__(e->cfg.device);
   if (!stats) return fail(DRL_ERR_INVALID, "drl_get_stats: null tensor");
   CUDA_TRY(cudaMemcpyAsync(stats, e->stats, DRL_STATS_COUNT * sizeof(double), cudaMemcpyDeviceToDevice,
                            (cudaStream_t)stream));
@@ -539,6 +556,7 @@ extern "C" int drl_get_stats(DrlEnv* e, double* stats, void* stream) {
 extern "C" int drl_reset_stats(DrlEnv* e, void* stream) {
   int rc = ready(e, "drl_reset_stats");
   if (rc) return rc;
+  DeviceGuard guard__(e->cfg.device);
   CUDA_TRY(cudaMemsetAsync(e->stats, 0, DRL_STATS_COUNT * sizeof(double), (cudaStream_t)stream));
   return DRL_OK;
 }
@@ -547,6 +565,7 @@ extern "C" int drl_get_episode_ring(DrlEnv* e, int32_t* ep_len, float* ep_ret, i
                                     int64_t* total_episodes, void* stream) {
   int rc = ready(e, "drl_get_episode_ring");
   if (rc) return rc;
+  DeviceGuard guard__(e->cfg.device);
   if (!total_episodes) return fail(DRL_ERR_INVALID, "drl_get_episode_ring: null argument");
   cudaStream_t st = (cudaStream_t)stream;
   unsigned long long head = 0;
@@ -563,6 +582,7 @@ extern "C" int drl_get_episode_positions(DrlEnv* e, int32_t* rsi_pos, int32_t* e
                                          int32_t capacity, void* stream) {
   int rc = ready(e, "drl_get_episode_positions");
   if (rc) return rc;
+  DeviceGuard guard__(e->cfg.device);
   cudaStream_t st = (cudaStream_t)stream;
   const int n = capacity < e->ring_cap ? capacity : e->ring_cap;
   if (n <= 0) return DRL_OK;
@@ -575,6 +595,7 @@ extern "C" int drl_get_episode_positions(DrlEnv* e, int32_t* rsi_pos, int32_t* e
 extern "C" int drl_get_running_rsi_positions(DrlEnv* e, int32_t* rsi_pos, void* stream) {
   int rc = ready(e, "drl_get_running_rsi_positions");
   if (rc) return rc;
+  DeviceGuard guard__(e->cfg.device);
   if (!rsi_pos) return fail(DRL_ERR_INVALID, "drl_get_running_rsi_positions: null tensor");
   CUDA_TRY(launch_running_rsi(e->state_i, rsi_pos, e->cfg.num_envs, (cudaStream_t)stream));
   return DRL_OK;
@@ -593,7 +614,7 @@ extern "C" int drl_set_det_init_counters(DrlEnv* e, const int32_t* counts) {
   for (int i = 0; i < n; i++)
     if (counts[i] < 0 || counts[i] >= (e->cfg.eval_n_times > 0 ? e->cfg.eval_n_times : 1))
       return fail(DRL_ERR_INVALID, "drl_set_det_init_counters: counts[%d] = %d outside [0, eval_n_times)", i, counts[i]);
-  CUDA_TRY(cudaSetDevice(e->cfg.device));
+  DeviceGuard guard__(e->cfg.device);
   CUDA_TRY(cudaDeviceSynchronize());
   CUDA_TRY(cudaMemcpy2D(e->state_i + kCurNDet, kCurCount8 * sizeof(int), counts, sizeof(int), sizeof(int), (size_t)n,
                         cudaMemcpyHostToDevice));
@@ -605,7 +626,7 @@ extern "C" int drl_set_seed(DrlEnv* e, uint64_t seed) {
   if (!e->have_model) return fail(DRL_ERR_STATE, "drl_set_seed: upload the model first");
   e->cfg.seed = seed;
   e->hm.seed = seed;
-  CUDA_TRY(cudaSetDevice(e->cfg.device));
+  DeviceGuard guard__(e->cfg.device);
   CUDA_TRY(cudaDeviceSynchronize());          // enqueued steps may still read the model block
   CUDA_TRY(cudaMemcpy(e->d_model, &e->hm, sizeof(DevModel), cudaMemcpyHostToDevice));
   return DRL_OK;
@@ -621,7 +642,7 @@ extern "C" int drl_set_speed_profile(DrlEnv* e, const float* speeds, int32_t n) 
   if (!e) return fail(DRL_ERR_INVALID, "drl_set_speed_profile: null env");
   if (n < 0 || (n > 0 && !speeds)) return fail(DRL_ERR_INVALID, "drl_set_speed_profile: n=%d with %s table", n,
                                                speeds ? "a" : "a null");
-  CUDA_TRY(cudaSetDevice(e->cfg.device));
+  DeviceGuard guard__(e->cfg.device);
   CUDA_TRY(cudaDeviceSynchronize());   // the previous table may still be read by enqueued steps
   if (e->speed_profile) CUDA_TRY(cudaFree(e->speed_profile));
   e->speed_profile = nullptr;
@@ -653,8 +674,8 @@ extern "C" int drl_debug_set(DrlEnv* e, int32_t frame_skip_override, int32_t blo
     if (block_threads % 32 != 0 || block_threads > 128) return fail(DRL_ERR_INVALID, "drl_debug_set: block size must be 32, 64, 96 or 128");
     e->block = block_threads;
   }
+  DeviceGuard guard__(e->cfg.device);
   if (enable_dump && !e->debug) {
-    cudaSetDevice(e->cfg.device);
     const size_t n = (size_t)e->cfg.num_envs * 32 * 40;
     CUDA_TRY(cudaMalloc(&e->debug, n * sizeof(float)));
     CUDA_TRY(cudaMemset(e->debug, 0, n * sizeof(float)));

@@ -36,6 +36,7 @@ struct Topo<14> {   // walker3d_flat_feet.xml: torso -> {right, left} x (thigh[2
   __host__ __device__ static constexpr int axis(int k, int s) { return k == 0 ? s : (k == 1 ? (s == 0 ? 1 : 0) : 1); }
   __host__ __device__ static constexpr int chain_of(int j) { return (j - 6) / 4; }     // for j >= NROOT
   static constexpr int NBOX = 2;
+  __host__ __device__ static constexpr int box_body(int bx) { return bx == 0 ? 3 : 6; }   // the feet
 };
 
 template <>
@@ -49,7 +50,23 @@ struct Topo<19> {   // walker_165cm_65kg.xml: pelvis -> {right, left} x (thigh[3
   __host__ __device__ static constexpr int axis(int k, int s) { return k == 0 ? s : (k == 1 ? (s == 2 ? 2 : -1) : 1); }
   __host__ __device__ static constexpr int chain_of(int j) { return j < 9 ? 2 : (j < 14 ? 0 : 1); }   // for j >= NROOT
   static constexpr int NBOX = 4;
+  __host__ __device__ static constexpr int box_body(int bx) { return bx == 0 ? 0 : (bx == 1 ? 1 : (bx == 2 ? 4 : 7)); }
 };
+
+// bodies of the subtree rooted at body b (bit mask), from the chain tables
+template <int NV>
+__host__ __device__ constexpr unsigned body_subtree_mask(int b) {
+  using T = Topo<NV>;
+  if (b == 0) return (1u << T::NB) - 1u;
+  unsigned m = 0;
+  for (int c = 0; c < T::NCHAIN; c++)
+    for (int k = 1; k < T::chain_len(c); k++) {
+      const int x = T::chain_body1(c) + k - 1;
+      if (x == b)
+        for (int k2 = k; k2 < T::chain_len(c); k2++) m |= 1u << (T::chain_body1(c) + k2 - 1);
+    }
+  return m;
+}
 
 // is dof r a strict ancestor of dof k (r moves the body k is attached to)?  The chains are serial, so: an earlier dof
 // of the root or of k's own chain.
@@ -404,7 +421,7 @@ __device__ __forceinline__ void mass_column2(const DevModel& M, EnvSmem2<G>& E, 
 template <int NV, int G, bool DBG>
 __device__ __forceinline__ void forward_dynamics2(const DevModel& M, EnvSmem2<G>& E, const LaneConst& L,
                                                   const ChainLane& C, float q, float v, float tau, float& a,
-                                                  ActiveSet& AS, Vec6& S, float* dbg) {
+                                                  ActiveSet& AS, Vec6& S, float* dbg, bool solver_barrier) {
   using T = Topo<NV>;
   const int l = L.l;
   const bool iscomp = l < 6 * T::NCHAIN;
@@ -584,79 +601,108 @@ __device__ __forceinline__ void forward_dynamics2(const DevModel& M, EnvSmem2<G>
   unsigned subcon = 0u;
 #pragma unroll
   for (int b = 0; b < T::NB; b++)
-    if (M.body_sub[b] & conmask) subcon |= 1u << b;
+    if (body_subtree_mask<NV>(b) & conmask) subcon |= 1u << b;
   int n_iter = 0;
   bool capped = false;
+  // Optional CTA barrier here instead of at the start of the evaluation (StepArgs::stage_barrier == 2): warps whose
+  // previous evaluation converged in one solver pass run ahead through the kinematics / bias-force half of this one
+  // while the others finish their extra pass, and the block lines up again for the solver (shared instruction stream).
+  if (solver_barrier) __syncthreads();
   float H[NV + 1];
   for (int it = 0; it < kMaxSolverIter; it++) {
     if (constrained) n_iter++;
     if (conmask != 0u) {
-      // Per-body accumulators W (21) / U (6).  Box bodies are written by their 8-lane segment (zeros when the segment
-      // has no active corner), capsule-only bodies are zeroed here and filled below; no atomics anywhere, so the
-      // result does not depend on scheduling.
-      if (sph_any) {
+      // Per-body accumulators W (21) / U (6), then their sums over subtrees.  Box corners: the 8 lanes of a segment
+      // belong to one box = one body.  Every corner lane stages the 27 numbers of its contact (wrench-space Hessian of
+      // the active pyramid rows + rhs wrench), then the lanes share out the 27 x (number of boxes) sums over the 8
+      // corners in a fixed order.  No atomics anywhere: the result does not depend on scheduling.
+      float wv[28];
+      contact_hessian(c0, act0 ? AS.bits[0] : 0u, wv);
+      if (l < M.nbox_cand) {
+        float* dst = &E.Wred[((l >> 3) * 27) * 8 + (l & 7)];
+#pragma unroll
+        for (int i = 0; i < 27; i++) dst[i * 8] = wv[i];
+      }
+      __syncwarp();
+      if (!sph_any) {
+        // common case (boxes only): the lane that sums entry i of every box also forms the subtree sums - body b
+        // receives the boxes of its subtree (compile-time subsets) - so no scan over the tree is needed
+#pragma unroll
+        for (int i0 = 0; i0 < 27; i0 += G) {
+          const int i = i0 + l;
+          if (i < 27) {
+            float sb[T::NBOX];
+#pragma unroll
+            for (int bx = 0; bx < T::NBOX; bx++) {
+              const float4 x0 = *reinterpret_cast<const float4*>(&E.Wred[(bx * 27 + i) * 8]);
+              const float4 x1 = *reinterpret_cast<const float4*>(&E.Wred[(bx * 27 + i) * 8 + 4]);
+              sb[bx] = ((x0.x + x0.y) + (x0.z + x0.w)) + ((x1.x + x1.y) + (x1.z + x1.w));
+            }
+#pragma unroll
+            for (int b = 0; b < T::NB; b++) {
+              float tot = 0.f;
+              bool any = false;
+#pragma unroll
+              for (int bx = 0; bx < T::NBOX; bx++)
+                if ((body_subtree_mask<NV>(b) >> T::box_body(bx)) & 1u) { tot = any ? tot + sb[bx] : sb[bx]; any = true; }
+              if (any) {
+                if (i < 21) E.W[b][i] = tot; else E.U[b][i - 21] = tot;
+              }
+            }
+          }
+        }
+        __syncwarp();
+      } else {
+        // a capsule touches the ground (fallen walker): per-body accumulators first, then the generic subtree scan
         for (unsigned mk = conmask & ~M.box_body_mask; mk; mk &= mk - 1) {
           const int b = __ffs(mk) - 1;
           for (int i = l; i < 24; i += G) E.W[b][i] = 0.f;
           if (l < 8) E.U[b][l] = 0.f;
         }
-      }
-      {
-        // box corners: the 8 lanes of a segment belong to one box = one body.  Every corner lane stages the 27 numbers
-        // of its contact (wrench-space Hessian of the active pyramid rows + rhs wrench), then the lanes share out the
-        // 27 x (number of boxes) sums over the 8 corners (fixed order: deterministic) and store the body's accumulators.
-        float wv[28];
-        contact_hessian(c0, act0 ? AS.bits[0] : 0u, wv);
-        if (l < M.nbox_cand) {
-          float* dst = &E.Wred[((l >> 3) * 27) * 8 + (l & 7)];
-#pragma unroll
-          for (int i = 0; i < 27; i++) dst[i * 8] = wv[i];
-        }
-        __syncwarp();
 #pragma unroll
         for (int bx = 0; bx < T::NBOX; bx++) {
 #pragma unroll
           for (int i0 = 0; i0 < 27; i0 += G) {
             const int i = i0 + l;
-            if (i < 27 && bx * 8 < M.nbox_cand) {
+            if (i < 27) {
               const float4 x0 = *reinterpret_cast<const float4*>(&E.Wred[(bx * 27 + i) * 8]);
               const float4 x1 = *reinterpret_cast<const float4*>(&E.Wred[(bx * 27 + i) * 8 + 4]);
               const float sum = ((x0.x + x0.y) + (x0.z + x0.w)) + ((x1.x + x1.y) + (x1.z + x1.w));
-              const int b = M.cand_body[bx * 8];
+              const int b = T::box_body(bx);
               if (i < 21) E.W[b][i] = sum; else E.U[b][i - 21] = sum;
             }
           }
         }
-      }
-      if (sph_any) {
-        // capsule end spheres: added one contact at a time in lane order (deterministic)
-        float wv[28];
-        Contact c1 = {0.f, 0.f, 0.f, 0.f, 0.f, {0.f, 0.f, 0.f, 0.f}};
-        const unsigned bt = act1 ? AS.bits[1] : 0u;
-        if (bt) c1 = ld_contact(E.sph[l]);
-        contact_hessian(c1, bt, wv);
-        const int b1 = M.cand_body[G + l < M.ncand ? G + l : 0];
-        __syncwarp();
-        for (unsigned sm = __ballot_sync(kFull, bt != 0u); sm; sm &= sm - 1) {
-          if (wl == __ffs(sm) - 1) {
-            float* Wb = E.W[b1];
-            float* Ub = E.U[b1];
-#pragma unroll
-            for (int i = 0; i < 21; i++) Wb[i] += wv[i];
-#pragma unroll
-            for (int i = 0; i < 6; i++) Ub[i] += wv[21 + i];
-          }
+        {
+          // capsule end spheres: added one contact at a time in lane order (deterministic)
+          float wv1[28];
+          Contact c1 = {0.f, 0.f, 0.f, 0.f, 0.f, {0.f, 0.f, 0.f, 0.f}};
+          const unsigned bt = act1 ? AS.bits[1] : 0u;
+          if (bt) c1 = ld_contact(E.sph[l]);
+          contact_hessian(c1, bt, wv1);
+          const int b1 = M.cand_body[G + l < M.ncand ? G + l : 0];
           __syncwarp();
+          for (unsigned sm = __ballot_sync(kFull, bt != 0u); sm; sm &= sm - 1) {
+            if (wl == __ffs(sm) - 1) {
+              float* Wb = E.W[b1];
+              float* Ub = E.U[b1];
+#pragma unroll
+              for (int i = 0; i < 21; i++) Wb[i] += wv1[i];
+#pragma unroll
+              for (int i = 0; i < 6; i++) Ub[i] += wv1[21 + i];
+            }
+            __syncwarp();
+          }
         }
+        __syncwarp();
+        // subtree sums of W (21 entries) and U (6): what the composite inertia / subtree force of every body gains
+        const unsigned present = conmask | M.box_body_mask;   // box bodies are always written (zeros without contact)
+        for (int i = l; i < 27; i += G) {
+          if (i < 21) subtree_scan<NV>(&E.W[0][i], &E.W[0][i], 24, present);
+          else subtree_scan<NV>(&E.U[0][i - 21], &E.U[0][i - 21], 8, present);
+        }
+        __syncwarp();
       }
-      __syncwarp();
-      // subtree sums of W (21 entries) and U (6): what the composite inertia / subtree force of every body gains
-      const unsigned present = conmask | M.box_body_mask;   // box bodies are always written (zeros without contact)
-      for (int i = l; i < 27; i += G) {
-        if (i < 21) subtree_scan<NV>(&E.W[0][i], &E.W[0][i], 24, present);
-        else subtree_scan<NV>(&E.U[0][i - 21], &E.U[0][i - 21], 8, present);
-      }
-      __syncwarp();
     }
     // (Ic + Wsub) S and the rhs of this lane's dof
     H[NV] = rhs0;

@@ -379,10 +379,10 @@ __global__ void __launch_bounds__(128, 4) mimic_step_kernel(const StepArgs A, co
         // keep the warps of a CTA within one evaluation of each other: they then share instruction-cache lines
         // (the dynamics evaluation is ~80 KB of straight-line code); measured +3 %
         // (one barrier per substep instead of per stage loses the gain; a second barrier inside the evaluation adds none)
-        if (A.stage_barrier) __syncthreads();
+        if (A.stage_barrier == 1) __syncthreads();
         if constexpr (FDV == 2) {
           Vec6 Sj;
-          forward_dynamics2<NV, G, DBG>(M, E, L, CL, q, v, tau, a, AS, Sj, dbgp);
+          forward_dynamics2<NV, G, DBG>(M, E, L, CL, q, v, tau, a, AS, Sj, dbgp, A.stage_barrier == 2);
         } else {
           forward_dynamics<NV, G, DBG>(M, E, L, q, v, tau, a, AS, cnt, dbgp);
         }
@@ -404,7 +404,7 @@ __global__ void __launch_bounds__(128, 4) mimic_step_kernel(const StepArgs A, co
       float Ma = 0.f;
       if constexpr (FDV == 2) {
         Vec6 Sj;
-        forward_dynamics2<NV, G, DBG>(M, E, L, CL, q, v, tau, a, AS, Sj, dbgp);
+        forward_dynamics2<NV, G, DBG>(M, E, L, CL, q, v, tau, a, AS, Sj, dbgp, false);
         pure_mass_column2<NV, G>(M, E, L, Sj, Hc);     // E.acc holds the constrained qacc of every dof
 #pragma unroll
         for (int r = 0; r < NV; r++) {

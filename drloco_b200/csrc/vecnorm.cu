@@ -170,8 +170,9 @@ extern "C" int drl_vecnorm_apply(const float* obs_in, float* obs_out, const floa
 // the critical path.  Two mailbox parities alternate: a rank can be at most one exchange ahead of its slowest peer,
 // because its next exchange needs that peer's next flag.
 //
-// sync_every = K > 1 (opt-in, not SB3 semantics): the moments are accumulated locally and exchanged / merged on every
-// K-th step only; the steps in between are normalised with the statistics of the last merge.
+// sync_every = K > 1 (opt-in, not SB3 semantics): the moments of "cycle" calls (the env steps) are accumulated locally
+// and exchanged / merged on every K-th such call only; the steps in between are normalised with the statistics of the
+// last merge.  "Immediate" calls (VecNormalize.reset) exchange their own moments at once and leave the cycle alone.
 // ---------------------------------------------------------------------------------------------------------------------
 constexpr int kMaxPeers = 8;
 constexpr int kMaxPayload = 2 * DRL_MAX_OBS + 3;
@@ -181,7 +182,8 @@ struct DrlComm {
   void* base = nullptr;                  // local mailbox allocation (exported): mail [2][world][payload] f64, flags [2][world] u64
   double* mail = nullptr;
   unsigned long long* flags = nullptr;
-  unsigned long long* step = nullptr;    // steps normalised so far (device-side: the chain is CUDA-graph capturable)
+  unsigned long long* step = nullptr;    // [2] device-side counters (the chain is CUDA-graph capturable): exchanges done so
+                                         // far (mailbox parity / flag value), cycle calls since the last merge
   unsigned* ticket = nullptr;
   double* pending = nullptr;             // [payload] moments accumulated since the last exchange
   void* peer_base[kMaxPeers] = {};
@@ -216,15 +218,17 @@ __global__ void __launch_bounds__(256) vecnorm_step_kernel(
     float clip_rew, float eps, int upd_obs, int upd_ret, int norm_obs, int norm_rew, const CommView cv) {
   __shared__ double s_tot[kMaxPayload];
   __shared__ float s_mean[DRL_MAX_OBS], s_inv[DRL_MAX_OBS + 1];
-  __shared__ unsigned long long s_sid;
+  __shared__ unsigned long long s_ctr[2];
   const int P = cv.payload;        // 2d + 3
-  if (threadIdx.x == 0) s_sid = *reinterpret_cast<volatile unsigned long long*>(cv.step);
+  if (threadIdx.x < 2) s_ctr[threadIdx.x] = reinterpret_cast<volatile unsigned long long*>(cv.step)[threadIdx.x];
   __syncthreads();
-  const unsigned long long sid = s_sid;
-  const int K = cv.sync_every;
+  const unsigned long long x = s_ctr[0];       // exchanges done so far
+  const unsigned long long cyc = s_ctr[1];     // cycle calls accumulated since the last merge
+  const int K = cv.sync_every;                 // K >= 1: cycle call; K == 0: immediate call
   const bool update = (upd_obs || upd_ret) && packed != nullptr;
-  const bool sync = update && ((sid + 1) % (unsigned long long)K == 0);
-  const bool fresh = (sid % (unsigned long long)K) == 0;      // nothing pending from earlier steps
+  const bool immediate = K == 0;
+  const bool sync = update && (immediate || cyc + 1 >= (unsigned long long)K);
+  const bool fresh = immediate || cyc == 0;    // nothing pending from earlier cycle calls (or not to be used)
   bool merged = false;
   if (update) {
     if (!sync) {
@@ -232,7 +236,6 @@ __global__ void __launch_bounds__(256) vecnorm_step_kernel(
         for (int t = threadIdx.x; t < P; t += blockDim.x) cv.pending[t] = (fresh ? 0.0 : cv.pending[t]) + packed[t];
     } else {
       if (cv.world > 1) {
-        const unsigned long long x = sid / (unsigned long long)K;     // exchange number
         const int par = (int)(x & 1ull);
         if (blockIdx.x == 0) {
           for (int t = threadIdx.x; t < P; t += blockDim.x) {
@@ -299,7 +302,10 @@ __global__ void __launch_bounds__(256) vecnorm_step_kernel(
   if (threadIdx.x == 0) {
     __threadfence();
     if (atomicAdd(cv.ticket, 1u) == gridDim.x - 1) {
-      *cv.step = sid + 1ull;
+      if (update) {
+        if (sync) cv.step[0] = x + 1ull;
+        if (!immediate) cv.step[1] = sync ? 0ull : cyc + 1ull;
+      }
       *cv.ticket = 0u;
       __threadfence();
     }
@@ -327,8 +333,8 @@ extern "C" int drl_comm_create(int32_t world, int32_t rank, int32_t obs_dim, Drl
   VN_TRY(cudaMemset(c->base, 0, mail_bytes + flag_bytes));
   c->mail = (double*)c->base;
   c->flags = (unsigned long long*)((char*)c->base + mail_bytes);
-  VN_TRY(cudaMalloc(&c->step, sizeof(unsigned long long)));
-  VN_TRY(cudaMemset(c->step, 0, sizeof(unsigned long long)));
+  VN_TRY(cudaMalloc(&c->step, 2 * sizeof(unsigned long long)));
+  VN_TRY(cudaMemset(c->step, 0, 2 * sizeof(unsigned long long)));
   VN_TRY(cudaMalloc(&c->ticket, sizeof(unsigned)));
   VN_TRY(cudaMemset(c->ticket, 0, sizeof(unsigned)));
   VN_TRY(cudaMalloc(&c->pending, c->payload * sizeof(double)));
@@ -383,7 +389,7 @@ extern "C" int drl_vecnorm_step(const float* obs_in, float* obs_out, const float
                                 DrlComm* c, int32_t sync_every, void* stream) {
   if (!obs_in || !obs_out || !rms_in || !rms_out || n <= 0 || d <= 0 || d > DRL_MAX_OBS || rms_in == rms_out || !c)
     return DRL_ERR_INVALID;
-  if (c->payload != 2 * d + 3 || !c->connected || sync_every < 1) return DRL_ERR_STATE;
+  if (c->payload != 2 * d + 3 || !c->connected || sync_every < 0) return DRL_ERR_STATE;
   drl::CommView cv;
   cv.world = c->world; cv.rank = c->rank; cv.payload = c->payload; cv.sync_every = sync_every;
   cv.mail = c->mail; cv.flags = c->flags; cv.step = c->step; cv.ticket = c->ticket; cv.pending = c->pending;

@@ -112,17 +112,25 @@ class PPO:
                         rew=torch.zeros(T, N, device=dev), done=torch.zeros(T, N, device=dev))
 
     def save(self, path: str) -> None:
-        """checkpoint of the learner (policy, optimiser, step counter); the env statistics are saved by the env itself
-        (reference utils.save_model, utils.py:175-184, writes an SB3 zip + a pickled VecNormalize)."""
-        with open(path, "wb") as f:           # explicit handle: torch.save would otherwise rewrite the file suffix rules
-            torch.save({"policy": self.policy.state_dict(), "optimizer": self.opt.state_dict(),
-                        "num_timesteps": self.num_timesteps, "cfg": dataclasses.asdict(self.cfg)}, f)
+        """checkpoint of the learner in the layout of SB3's model zip (reference utils.save_model, utils.py:175-184:
+        ``models/model_<ckpt>.zip``): policy state dict under SB3's key names, optimiser state, step counter and
+        hyper-parameters in the json ``data`` entry.  The env statistics are saved by the env itself."""
+        from .checkpoint import save_sb3_zip
+        save_sb3_zip(path, self.policy, self.opt, data={"num_timesteps": int(self.num_timesteps),
+                                                        "ppo_config": dataclasses.asdict(self.cfg)})
 
     def load(self, path: str) -> "PPO":
-        ck = torch.load(path, map_location=self.device, weights_only=False)
-        self.policy.load_state_dict(ck["policy"])
-        self.opt.load_state_dict(ck["optimizer"])
-        self.num_timesteps = int(ck["num_timesteps"])
+        import io
+        import zipfile
+        from .checkpoint import load_sb3_zip
+        data = load_sb3_zip(path, self.policy, map_location=self.device)
+        with zipfile.ZipFile(path) as z:
+            if "policy.optimizer.pth" in z.namelist():
+                osd = torch.load(io.BytesIO(z.read("policy.optimizer.pth")), map_location=self.device,
+                                 weights_only=True)
+                if osd.get("param_groups"):
+                    self.opt.load_state_dict(osd)
+        self.num_timesteps = int(data.get("num_timesteps", self.num_timesteps))
         return self
 
     def _lr(self) -> float:                                            # schedules.py:16-33 LinearDecay

@@ -85,6 +85,7 @@ class TrainingMonitor:
         self.failed_eval_runs_indices: List[int] = []
         self.skip_n_steps, self.skipped_steps = 100, 99        # log every 101st call; the second call is the first that logs
         self.saved: List[str] = []          # checkpoints kept on disk (model paths)
+        self._last_ep_lens_reset_mio = -1      # the reference also empties the list on its very first call
 
     # -- callback.py:52-60
     def on_training_start(self) -> None:
@@ -100,8 +101,12 @@ class TrainingMonitor:
     # -- callback.py:62-122
     def on_step(self) -> bool:
         self.num_timesteps += self.n_envs
-        # distribution of the episode lengths of the last ~1M steps, not of the whole training
-        if self.num_timesteps % 1e6 < 1000:
+        # distribution of the episode lengths of the last ~1M steps, not of the whole training.  The reference tests
+        # `num_timesteps % 1e6 < 1000` with 8 envs per call (callback.py:69-70); with thousands of envs per call that
+        # window would be skipped most of the time, so the crossing of a 1M boundary is tracked explicitly.
+        mio = int(self.num_timesteps // 1e6)
+        if mio > self._last_ep_lens_reset_mio:
+            self._last_ep_lens_reset_mio = mio
             self.env.set_attr("ep_lens", [])
         self.n_steps_after_eval += 1 * self.n_envs
         if self.skipped_steps < self.skip_n_steps:

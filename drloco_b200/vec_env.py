@@ -581,6 +581,7 @@ class B200VecNormalize:
         self.launches = 0
         self._calls = 0                        # normalisation calls so far (host mirror of the device step counter)
         self._pending = None                   # exchange == "nccl" with stats_sync_every > 1: host-managed accumulation
+        self._cycle = 0
         self._comm = C.c_void_p()
         self.exchange = self._setup_exchange(exchange)
         lib.check(self._lib.drl_attach_vecnorm(venv._handle, _ptr(self.ret), float(self.gamma),
@@ -645,7 +646,7 @@ class B200VecNormalize:
         lib.check(self._lib.drl_attach_vecnorm(self.venv._handle, _ptr(self.ret), float(self.gamma),
                                                _ptr(self._packed[self._k ^ 1])), "drl_attach_vecnorm")
 
-    def _normalize(self, obs, rew, done, wait=True, packed=None, upd_obs=None, upd_ret=None):
+    def _normalize(self, obs, rew, done, wait=True, packed=None, upd_obs=None, upd_ret=None, immediate=False):
         """enqueue the exchange + merge + normalisation kernel for the env outputs just produced on the current stream.
         wait=True makes the current stream wait for the result (normal use); wait=False leaves it running on the side
         stream (``synchronize()`` / the next ``wait=True`` call / a stream sync picks it up)."""
@@ -670,17 +671,19 @@ class B200VecNormalize:
         with torch.cuda.device(self.device), torch.cuda.stream(stream):
             if not wait:
                 self._side.wait_event(ready)
-            sync_every = K
+            sync_every = 0 if immediate else K        # 0: exchange these moments now, outside the K-cycle (reset)
             if self.exchange == "nccl" and (upd_obs or upd_ret):
                 # host-issued collective: the kernel then sees a single-rank exchange of already reduced moments
-                sync_every = 1
-                if K > 1:
+                sync_every = 0
+                if K > 1 and not immediate:
                     if self._pending is None:
                         self._pending = torch.zeros_like(packed)
                     self._pending += packed
-                    if (self._calls + 1) % K == 0:
+                    self._cycle += 1
+                    if self._cycle >= K:
                         packed = self._pending.clone()
                         self._pending.zero_()
+                        self._cycle = 0
                     else:
                         upd_obs = upd_ret = False
                 if upd_obs or upd_ret:
@@ -730,13 +733,13 @@ class B200VecNormalize:
                 lib.check(self._lib.drl_vecnorm_moments(_ptr(obs), self.num_envs, D, None, None, float(self.gamma),
                                                         _ptr(pk), self.venv._stream()), "drl_vecnorm_moments")
             self.launches += 1
-            self._normalize(obs, None, None, packed=pk, upd_obs=self.training, upd_ret=False)
+            self._normalize(obs, None, None, packed=pk, upd_obs=self.training, upd_ret=False, immediate=True)
         else:
             # SB3 1.0 VecNormalize.reset: self.ret = zeros; if training: ret_rms.update(self.ret)
             pk = self._packed_reset
             pk.zero_()
             pk[2 * D] = float(self.num_envs)
-            self._normalize(obs, None, None, packed=pk, upd_obs=False, upd_ret=self.training)
+            self._normalize(obs, None, None, packed=pk, upd_obs=False, upd_ret=self.training, immediate=True)
         return self.norm_obs_buf
 
     def step_tensor(self, actions, inject=None, wait=True):
@@ -798,7 +801,7 @@ class B200VecNormalize:
     def _graph_key(self):
         v = self.venv
         return (v._cur, self._k, self._cur, self._hk, bool(self.training), bool(self.norm_obs), bool(self.norm_reward),
-                float(self.clip_obs), float(self.clip_reward), v._config_epoch, self._calls % self.stats_sync_every)
+                float(self.clip_obs), float(self.clip_reward), v._config_epoch, self.stats_sync_every)
 
     def step_async(self, actions, inject=None):
         self._host_buffers()

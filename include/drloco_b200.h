@@ -270,9 +270,10 @@ int drl_vecnorm_apply(const float* obs_in, float* obs_out, const float* rew_in, 
  * drl_vecnorm_step: exchange (peer stores into the mailboxes over NVLink + flags, summed in rank order: identical bits
  *   on every rank) + Chan merge into rms (rms_in -> rms_out, must not alias) + normalisation of obs / rew +
  *   ret[done] = 0.  flags: bit0 update the observation statistics, bit1 norm_obs, bit2 norm_reward, bit3 update the
- *   return statistics.  packed == NULL or no update bit: normalise only.  sync_every = K > 1 accumulates the moments
- *   locally and exchanges / merges on every K-th call only (opt-in amortisation; SB3 merges every step).  All ranks
- *   must make the same sequence of calls.  Asynchronous on `stream`; CUDA-graph capturable (the step counter lives on
+ *   return statistics.  packed == NULL or no update bit: normalise only.  sync_every = K >= 1: a "cycle" call - the
+ *   moments are accumulated locally and exchanged / merged on every K-th cycle call (K = 1: every call, SB3's
+ *   semantics; K > 1 is an opt-in amortisation); sync_every = 0: an "immediate" call - exchange and merge `packed` now,
+ *   leaving the cycle alone (VecNormalize.reset).  All ranks must make the same sequence of calls.  Asynchronous on `stream`; CUDA-graph capturable (the step counter lives on
  *   the device). */
 typedef struct DrlComm DrlComm;
 int drl_attach_vecnorm(DrlEnv* env, float* ret, float gamma, double* packed);

@@ -9,7 +9,7 @@ import ctypes as C
 
 import numpy as np
 
-DRL_ABI_VERSION = 1
+DRL_ABI_VERSION = 2
 MAX_DOF, MAX_BODY, MAX_ACT, MAX_SPHERE, MAX_BOX, MAX_SITE, MAX_OBS, MAX_PHASE_JOINTS = 24, 12, 16, 16, 8, 16, 64, 4
 INTEGRATOR_RK4, INTEGRATOR_EULER = 0, 1
 CURSOR_STEPWISE, CURSOR_WRAP = 0, 1
@@ -56,7 +56,7 @@ class DrlConfig(C.Structure):
         ("obs_dim", i32), ("act_dim", i32),
         ("mirror_obs_idx", i32 * MAX_OBS), ("mirror_obs_sign", C.c_float * MAX_OBS),
         ("mirror_act_idx", i32 * MAX_ACT), ("mirror_act_sign", C.c_float * MAX_ACT),
-        ("lanes_per_env", i32), ("early_termination", i32),
+        ("lanes_per_env", i32), ("early_termination", i32), ("monitor_median_torque", i32),
     ]
 
 

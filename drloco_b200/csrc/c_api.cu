@@ -87,6 +87,8 @@ struct DrlEnv {
   // 1 = fd_v1.cuh) and the per-evaluation CTA barrier; A/B runs of kernel variants without rebuilding
   int fd_version = 2;
   int stage_barrier = 1;
+  float* tor_hist = nullptr;
+  float* med_tor_sm = nullptr;
   // per-step statistics rows (one per thread block of the step kernel) + the ticket that elects the summing block
   double* cta_rows = nullptr;
   unsigned* cta_ticket = nullptr;
@@ -130,7 +132,7 @@ extern "C" int drl_destroy(DrlEnv* e) {
   void* ptrs[] = {e->d_model, e->state_f, e->state_i, e->state_as, e->state_d, e->extras_last, e->stats, e->ref, e->step_vel,
                   e->step_last_comx, e->des_vel_prefix, e->step_off, e->step_len, e->left_step, e->ring_len,
                   e->ring_ret, e->ring_head, e->debug, e->speed_profile, e->ring_rsi_pos, e->ring_et_pos, e->ring_difficult,
-                  e->cta_rows, e->cta_ticket};
+                  e->cta_rows, e->cta_ticket, e->tor_hist, e->med_tor_sm};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   delete e;
@@ -153,6 +155,13 @@ static int alloc_state(DrlEnv* e, size_t N) {
   CUDA_TRY(cudaMalloc(&e->ring_et_pos, e->ring_cap * sizeof(int)));
   CUDA_TRY(cudaMalloc(&e->ring_difficult, e->ring_cap));
   CUDA_TRY(cudaMalloc(&e->ring_head, sizeof(unsigned long long)));
+  if (e->cfg.monitor_median_torque) {
+    const size_t cap = (size_t)(e->cfg.ep_dur_max > 0 ? e->cfg.ep_dur_max : 1);
+    CUDA_TRY(cudaMalloc(&e->tor_hist, N * cap * sizeof(float)));
+    CUDA_TRY(cudaMemset(e->tor_hist, 0, N * cap * sizeof(float)));
+    CUDA_TRY(cudaMalloc(&e->med_tor_sm, N * sizeof(float)));
+    CUDA_TRY(cudaMemset(e->med_tor_sm, 0, N * sizeof(float)));
+  }
   {
     // the smallest CTA the library launches carries 32 / G environments
     const size_t max_blocks = (N + (32 / e->G) - 1) / (32 / e->G);
@@ -178,7 +187,8 @@ static void free_state(DrlEnv* e) {
   void** ptrs[] = {(void**)&e->d_model, (void**)&e->state_f, (void**)&e->state_i, (void**)&e->state_as,
                    (void**)&e->state_d, (void**)&e->extras_last, (void**)&e->stats, (void**)&e->ring_len,
                    (void**)&e->ring_ret, (void**)&e->ring_head, (void**)&e->ring_rsi_pos, (void**)&e->ring_et_pos,
-                   (void**)&e->ring_difficult, (void**)&e->cta_rows, (void**)&e->cta_ticket};
+                   (void**)&e->ring_difficult, (void**)&e->cta_rows, (void**)&e->cta_ticket,
+                   (void**)&e->tor_hist, (void**)&e->med_tor_sm};
   for (void** p : ptrs) {
     if (*p) cudaFree(*p);
     *p = nullptr;
@@ -473,6 +483,7 @@ static StepArgs make_args(DrlEnv* e) {
   a.playback = e->playback;
   a.stage_barrier = e->stage_barrier;
   a.cta_rows = e->cta_rows; a.cta_ticket = e->cta_ticket;
+  a.tor_hist = e->tor_hist; a.med_tor_sm = e->med_tor_sm;
   a.vn_ret = e->vn_ret; a.vn_gamma = e->vn_gamma; a.packed = e->vn_packed;
   if (e->playback) a.frame_skip = 0;
   a.debug = e->debug;
@@ -598,6 +609,17 @@ extern "C" int drl_get_running_rsi_positions(DrlEnv* e, int32_t* rsi_pos, void* 
   DeviceGuard guard__(e->cfg.device);
   if (!rsi_pos) return fail(DRL_ERR_INVALID, "drl_get_running_rsi_positions: null tensor");
   CUDA_TRY(launch_running_rsi(e->state_i, rsi_pos, e->cfg.num_envs, (cudaStream_t)stream));
+  return DRL_OK;
+}
+
+extern "C" int drl_get_median_torque(DrlEnv* e, float* out, void* stream) {
+  int rc = ready(e, "drl_get_median_torque");
+  if (rc) return rc;
+  DeviceGuard guard__(e->cfg.device);
+  if (!out) return fail(DRL_ERR_INVALID, "drl_get_median_torque: null tensor");
+  if (!e->med_tor_sm) return fail(DRL_ERR_STATE, "drl_get_median_torque: the env was created with monitor_median_torque = 0");
+  CUDA_TRY(cudaMemcpyAsync(out, e->med_tor_sm, (size_t)e->cfg.num_envs * sizeof(float), cudaMemcpyDeviceToDevice,
+                           (cudaStream_t)stream));
   return DRL_OK;
 }
 

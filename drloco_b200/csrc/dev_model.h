@@ -120,6 +120,9 @@ struct StepArgs {
   int playback;                      // kinematic playback: the state is set from the mocap instead of simulated
   int stage_barrier;                 // CTA barrier before every dynamics evaluation (instruction-cache sharing)
   float* debug;                      // nullable: per-env dump of one forward evaluation (tests)
+  // Monitor.median_abs_torque_smoothed (monitor_wrapper.py:131): per-episode history of the mean |torque| of every step
+  float* tor_hist;                   // [N][ep_dur_max], nullable (DrlConfig.monitor_median_torque)
+  float* med_tor_sm;                 // [N] smoothed median, written at episode ends
   // per-step statistics without atomics: every thread block writes one row of sums, the last block to finish adds them
   double* cta_rows;                  // [grid][2*obs_dim + 2 + DRL_STATS_COUNT]
   unsigned* cta_ticket;

@@ -127,8 +127,17 @@ __device__ __forceinline__ float ldl_solve_tree(float (&H)[NV + 1], int l) {
   return x;
 }
 
+// Staging layout of the per-corner contact Hessians: corner c of box bx, entry i lives at
+//   (c >> 2) * kWredHalf + (bx * kWredBox + i) * 4 + (c & 3)
+// so that the summing lane reads two conflict-free float4 (corners 0-3, 4-7) and the strides keep the eight lanes of a
+// box, the boxes and the two environments of a warp (8 banks apart) on different banks: box stride = 20 and half = 16
+// (mod 32 floats).
+constexpr int kWredBox = 29;                         // entries reserved per box (27 used)
+
 template <int G>
 struct EnvSmem2 {
+  static constexpr int kWredHalf = (G == 16 ? 2 * kWredBox * 4 + 8 : 4 * kWredBox * 4);
+  static_assert(kWredHalf % 32 == 16, "bank layout of the staging buffer");
   float v[G];               // qvel at the current stage
   float acc[G];             // qacc iterate
   float tau[G];             // actuator force per dof
@@ -146,7 +155,7 @@ struct EnvSmem2 {
     // and consumed at the start of a solver pass (Fd is rewritten right after); sph = the touching capsule-end contacts
     // of each lane (rare), which persist over the solver passes and therefore sit behind Wred, clear of Fd.
     struct {
-      float Wred[(G == 16 ? 2 : 4) * 27 * 8];
+      float Wred[2 * kWredHalf];
       float sph[G][12];
     };
   };
@@ -165,7 +174,11 @@ struct EnvSmem2 {
   };
   float obsbuf[kMaxObs];
   int cnt[4];               // solver passes, capped evaluations of this control step (statistics)
+  // pad the per-environment stride to 8 (mod 32) floats: the two environments of a warp then use disjoint banks in the
+  // chain scans (six components per chain, chains 16 banks apart)
+  float pad_[(G == 16) ? 20 : 4];
 };
+static_assert((sizeof(EnvSmem2<16>) / 4) % 32 == 8, "environment stride must be 8 mod 32 floats (bank layout)");
 static_assert(sizeof(EnvSmem2<16>) % 16 == 0 && sizeof(EnvSmem2<32>) % 16 == 0, "vector loads need 16-byte rows");
 
 // lane roles that depend on the chain layout (constant over the launch)
@@ -423,6 +436,7 @@ __device__ __forceinline__ void forward_dynamics2(const DevModel& M, EnvSmem2<G>
                                                   const ChainLane& C, float q, float v, float tau, float& a,
                                                   ActiveSet& AS, Vec6& S, float* dbg, bool solver_barrier) {
   using T = Topo<NV>;
+  using ES = EnvSmem2<G>;
   const int l = L.l;
   const bool iscomp = l < 6 * T::NCHAIN;
   // ---- 1. joint trig + velocity ------------------------------------------------------------------------------------
@@ -619,9 +633,9 @@ __device__ __forceinline__ void forward_dynamics2(const DevModel& M, EnvSmem2<G>
       float wv[28];
       contact_hessian(c0, act0 ? AS.bits[0] : 0u, wv);
       if (l < M.nbox_cand) {
-        float* dst = &E.Wred[((l >> 3) * 27) * 8 + (l & 7)];
+        float* dst = &E.Wred[((l >> 2) & 1) * ES::kWredHalf + (l >> 3) * kWredBox * 4 + (l & 3)];
 #pragma unroll
-        for (int i = 0; i < 27; i++) dst[i * 8] = wv[i];
+        for (int i = 0; i < 27; i++) dst[i * 4] = wv[i];
       }
       __syncwarp();
       if (!sph_any) {
@@ -634,8 +648,8 @@ __device__ __forceinline__ void forward_dynamics2(const DevModel& M, EnvSmem2<G>
             float sb[T::NBOX];
 #pragma unroll
             for (int bx = 0; bx < T::NBOX; bx++) {
-              const float4 x0 = *reinterpret_cast<const float4*>(&E.Wred[(bx * 27 + i) * 8]);
-              const float4 x1 = *reinterpret_cast<const float4*>(&E.Wred[(bx * 27 + i) * 8 + 4]);
+              const float4 x0 = *reinterpret_cast<const float4*>(&E.Wred[(bx * kWredBox + i) * 4]);
+              const float4 x1 = *reinterpret_cast<const float4*>(&E.Wred[ES::kWredHalf + (bx * kWredBox + i) * 4]);
               sb[bx] = ((x0.x + x0.y) + (x0.z + x0.w)) + ((x1.x + x1.y) + (x1.z + x1.w));
             }
 #pragma unroll
@@ -665,8 +679,8 @@ __device__ __forceinline__ void forward_dynamics2(const DevModel& M, EnvSmem2<G>
           for (int i0 = 0; i0 < 27; i0 += G) {
             const int i = i0 + l;
             if (i < 27) {
-              const float4 x0 = *reinterpret_cast<const float4*>(&E.Wred[(bx * 27 + i) * 8]);
-              const float4 x1 = *reinterpret_cast<const float4*>(&E.Wred[(bx * 27 + i) * 8 + 4]);
+              const float4 x0 = *reinterpret_cast<const float4*>(&E.Wred[(bx * kWredBox + i) * 4]);
+              const float4 x1 = *reinterpret_cast<const float4*>(&E.Wred[ES::kWredHalf + (bx * kWredBox + i) * 4]);
               const float sum = ((x0.x + x0.y) + (x0.z + x0.w)) + ((x1.x + x1.y) + (x1.z + x1.w));
               const int b = T::box_body(bx);
               if (i < 21) E.W[b][i] = sum; else E.U[b][i - 21] = sum;

@@ -101,6 +101,39 @@ __device__ __forceinline__ float group_min(float x) {
   return x;
 }
 
+template <int G>
+__device__ __forceinline__ int group_sum_int(int x) {
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) x += __shfl_xor_sync(kFull, x, o);
+  return x;
+}
+
+// np.median of the first n entries of hist (non-negative floats), computed by the G lanes of an environment with a
+// bitwise radix select (31 counting passes per order statistic).  Called by every lane of the warp; n may differ
+// between the two environments of a warp, n == 0 returns 0.  Runs once per finished episode (Monitor.step,
+// monitor_wrapper.py:131).
+template <int G>
+__device__ __noinline__ float group_median(const float* __restrict__ hist, int n, int l) {
+  const int nmax = __reduce_max_sync(kFull, n);
+  float res[2] = {0.f, 0.f};
+#pragma unroll 1
+  for (int which = 0; which < 2; which++) {
+    const int k = which == 0 ? (n - 1) / 2 : n / 2;       // lower / upper middle (equal for odd n)
+    unsigned prefix = 0u;
+#pragma unroll 1
+    for (int bit = 30; bit >= 0; bit--) {
+      const unsigned cand = prefix | (1u << bit);
+      int cnt = 0;
+      for (int i = l; i < nmax; i += G)
+        if (i < n && __float_as_uint(hist[i]) < cand) cnt++;
+      cnt = group_sum_int<G>(cnt);
+      if (cnt <= k) prefix = cand;
+    }
+    res[which] = __uint_as_float(prefix);
+  }
+  return n > 0 ? 0.5f * (res[0] + res[1]) : 0.f;
+}
+
 // desired walking velocity vector (straight:417-422,479-480 / loco3d:51-97)
 __device__ __forceinline__ void desired_velocity(const DevModel& M, const StepArgs& A, const Cursor& c, float& d0,
                                                  float& d1) {
@@ -514,6 +547,18 @@ __global__ void __launch_bounds__(128, 4) mimic_step_kernel(const StepArgs A, co
   // ---- Monitor.step (monitor_wrapper.py:88-166) --------------------------------------------------------------------
   ep_ret += reward;
   ep_tor += mean_abs_torque;
+  const int ep_len_now = bad ? ep_dur_before + 1 : c.ep_dur;
+  // per-episode history of the mean |torque| for Monitor's median statistic (monitor_wrapper.py:102,131)
+  float med_tor = 0.f;
+  if (A.tor_hist) {
+    float* hist = A.tor_hist + (size_t)env * M.ep_dur_max;
+    if (l == 0 && live && ep_dur_before < M.ep_dur_max) hist[ep_dur_before] = mean_abs_torque;
+    __syncwarp();
+    if (__any_sync(kFull, done)) {
+      const int nh = ep_len_now < M.ep_dur_max ? ep_len_now : M.ep_dur_max;
+      med_tor = group_median<G>(hist, (done && live) ? nh : 0, l);
+    }
+  }
   double* sd = A.state_d + (size_t)env * 4;
   if (l == 0 && live) {
     sd[0] += (double)pos_rew; sd[1] += (double)vel_rew; sd[2] += (double)com_rew; sd[3] += 1.0;
@@ -552,7 +597,7 @@ __global__ void __launch_bounds__(128, 4) mimic_step_kernel(const StepArgs A, co
     }
   }
   if (done && l == 0 && live) {
-    const int ep_len = bad ? ep_dur_before + 1 : c.ep_dur;
+    const int ep_len = ep_len_now;
     float* ms = sf + 3 * G;
     const int fl = c.flags;
     auto smooth = [&](int slot, int bit, float nv, float f) {
@@ -565,6 +610,7 @@ __global__ void __launch_bounds__(128, 4) mimic_step_kernel(const StepArgs A, co
     smooth(kMiscEpRetSm, 1, ep_ret, 0.25f);
     smooth(kMiscEpLenSm, 1, (float)ep_len, 0.75f);
     smooth(kMiscTorSm, 1, ep_tor / (float)ep_len, 0.75f);
+    if (A.tor_hist) A.med_tor_sm[env] = (fl >> 1) & 1 ? 0.75f * med_tor + 0.25f * A.med_tor_sm[env] : med_tor;
     c.flags |= 2;
     ms[kMiscMoved] = walked;
     srow[kRowStats + DRL_STAT_EPISODES] = 1.0;
@@ -730,6 +776,11 @@ __global__ void state_copy_kernel(float* state_f, int* state_i, int* state_as, f
 // ------------------------------------------------------------------------------------------------------------------
 // launch helpers used by c_api.cu
 // ------------------------------------------------------------------------------------------------------------------
+// BASELINE.json configs[1] (4096 walker3d envs = 27.7 envs per SM) is one wave only if four 128-thread blocks fit an SM:
+// 4 x (model + 8 environments + 1 KB reserved) <= 228 KB
+static_assert(4 * ((sizeof(DevModel) + 15) / 16 * 16 + 8 * sizeof(EnvSmem2<16>) + 1024) <= 228 * 1024,
+              "walker3d: four blocks per SM must fit in shared memory");
+
 size_t step_smem_bytes(int G, int envs_per_block, int fdv) {
   const size_t model = (sizeof(DevModel) + 15) / 16 * 16;
   const size_t per_env = fdv == 2 ? (G == 16 ? sizeof(EnvSmem2<16>) : sizeof(EnvSmem2<32>))

@@ -214,8 +214,9 @@ __device__ __forceinline__ void st_flag(unsigned long long* p, unsigned long lon
 __global__ void __launch_bounds__(256) vecnorm_step_kernel(
     const float* __restrict__ obs_in, float* __restrict__ obs_out, const float* __restrict__ rew_in,
     float* __restrict__ rew_out, int n, int d, const double* __restrict__ packed, const double* __restrict__ rms_in,
-    double* __restrict__ rms_out, float* __restrict__ ret, const unsigned char* __restrict__ done, float clip_obs,
-    float clip_rew, float eps, int upd_obs, int upd_ret, int norm_obs, int norm_rew, const CommView cv) {
+    double* __restrict__ rms_out, float* __restrict__ ret, const unsigned char* __restrict__ done,
+    unsigned char* __restrict__ done_out, float clip_obs, float clip_rew, float eps, int upd_obs, int upd_ret,
+    int norm_obs, int norm_rew, const CommView cv) {
   __shared__ double s_tot[kMaxPayload];
   __shared__ float s_mean[DRL_MAX_OBS], s_inv[DRL_MAX_OBS + 1];
   __shared__ unsigned long long s_ctr[2];
@@ -297,6 +298,8 @@ __global__ void __launch_bounds__(256) vecnorm_step_kernel(
       if (done != nullptr && done[i]) ret[i] = 0.f;
     }
   }
+  if (done != nullptr && done_out != nullptr)       // the flags travel with the normalised outputs (one host copy)
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) done_out[i] = done[i];
   // the last block to finish advances the step counter (every block has read it by then)
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -385,8 +388,8 @@ extern "C" int drl_comm_destroy(DrlComm* c) {
 // flags: bit0 update the observation statistics, bit1 norm_obs, bit2 norm_reward, bit3 update the return statistics
 extern "C" int drl_vecnorm_step(const float* obs_in, float* obs_out, const float* rew_in, float* rew_out, int32_t n,
                                 int32_t d, const double* packed, const double* rms_in, double* rms_out, float* ret,
-                                const uint8_t* done, float clip_obs, float clip_rew, float eps, int32_t flags,
-                                DrlComm* c, int32_t sync_every, void* stream) {
+                                const uint8_t* done, uint8_t* done_out, float clip_obs, float clip_rew, float eps,
+                                int32_t flags, DrlComm* c, int32_t sync_every, void* stream) {
   if (!obs_in || !obs_out || !rms_in || !rms_out || n <= 0 || d <= 0 || d > DRL_MAX_OBS || rms_in == rms_out || !c)
     return DRL_ERR_INVALID;
   if (c->payload != 2 * d + 3 || !c->connected || sync_every < 0) return DRL_ERR_STATE;
@@ -403,8 +406,8 @@ extern "C" int drl_vecnorm_step(const float* obs_in, float* obs_out, const float
   if (blocks < 1) blocks = 1;
   if (blocks > 148 * 4) blocks = 148 * 4;      // every block waits for the peers' flags: keep the grid resident
   drl::vecnorm_step_kernel<<<blocks, drl::kVnThreads, 0, (cudaStream_t)stream>>>(
-      obs_in, obs_out, rew_in, rew_out, n, d, packed, rms_in, rms_out, ret, done, clip_obs, clip_rew, eps, flags & 1,
-      (flags >> 3) & 1, (flags >> 1) & 1, (flags >> 2) & 1, cv);
+      obs_in, obs_out, rew_in, rew_out, n, d, packed, rms_in, rms_out, ret, done, done_out, clip_obs, clip_rew, eps,
+      flags & 1, (flags >> 3) & 1, (flags >> 1) & 1, (flags >> 2) & 1, cv);
   return cudaGetLastError() == cudaSuccess ? DRL_OK : DRL_ERR_CUDA;
 }
 

@@ -34,6 +34,7 @@ PROTOTYPES = {
     "drl_get_episode_ring": (C.c_int, [vp, vp, vp, i32, C.POINTER(C.c_int64), vp]),
     "drl_get_episode_positions": (C.c_int, [vp, vp, vp, vp, i32, vp]),
     "drl_get_running_rsi_positions": (C.c_int, [vp, vp, vp]),
+    "drl_get_median_torque": (C.c_int, [vp, vp, vp]),
     "drl_set_eval_mode": (C.c_int, [vp, i32]),
     "drl_set_det_init_counters": (C.c_int, [vp, vp]),
     "drl_set_speed_profile": (C.c_int, [vp, vp, i32]),
@@ -47,7 +48,7 @@ PROTOTYPES = {
     "drl_comm_export": (C.c_int, [vp, vp]),
     "drl_comm_connect": (C.c_int, [vp, vp]),
     "drl_comm_destroy": (C.c_int, [vp]),
-    "drl_vecnorm_step": (C.c_int, [vp, vp, vp, vp, i32, i32, vp, vp, vp, vp, vp, f32, f32, f32, i32, vp, i32, vp]),
+    "drl_vecnorm_step": (C.c_int, [vp, vp, vp, vp, i32, i32, vp, vp, vp, vp, vp, vp, f32, f32, f32, i32, vp, i32, vp]),
     "drl_vecnorm_terminal": (C.c_int, [vp, vp, vp, i32, i32, vp, f32, f32, i32, vp]),
     "drl_vecnorm_terminal_compact": (C.c_int, [vp, vp, i32, i32, vp, f32, f32, i32, vp, vp]),
     "drl_fp32_peak_probe": (C.c_int, [i32, C.POINTER(C.c_double)]),

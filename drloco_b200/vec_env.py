@@ -84,12 +84,26 @@ class _TerminalRows:
 
     PREFIX = 256
 
-    def __init__(self, n: int, d: int, device):
+    def __init__(self, n: int, d: int, device, dev_words=None, host_words=None):
+        """dev_words / host_words: views of a larger output pack (B200VecNormalize) - the device view holds all records,
+        the pinned host view at least the prefix; None: own buffers, own prefix copy."""
         self.n, self.d, self.device = n, d, device
-        self.words = 4 + n * (d + 1)
-        self.dev = torch.zeros(self.words, dtype=torch.float32, device=device)
-        self.npre = 4 + min(n, self.PREFIX) * (d + 1)
-        self.host = torch.zeros(self.words, dtype=torch.float32).pin_memory()
+        self.words = self.words_for(n, d)
+        self.npre = self.prefix_words(n, d)
+        self.own_copy = dev_words is None
+        self.dev = torch.zeros(self.words, dtype=torch.float32, device=device) if dev_words is None else dev_words
+        self.set_host(torch.zeros(self.words, dtype=torch.float32).pin_memory() if host_words is None else host_words)
+
+    @staticmethod
+    def words_for(n, d):
+        return 4 + n * (d + 1)
+
+    @classmethod
+    def prefix_words(cls, n, d):
+        return 4 + min(n, cls.PREFIX) * (d + 1)
+
+    def set_host(self, host_words):
+        self.host = host_words
         self.host_np = self.host.numpy()
         self.host_i = self.host_np.view(np.int32)
 
@@ -97,7 +111,8 @@ class _TerminalRows:
         lib.check(libh.drl_vecnorm_terminal_compact(_ptr(tobs), _ptr(done), self.n, self.d, _ptr(rms), float(clip_obs),
                                                     float(eps), int(norm_obs), _ptr(self.dev), stream_ptr),
                   "drl_vecnorm_terminal_compact")
-        self.host[:self.npre].copy_(self.dev[:self.npre], non_blocking=True)
+        if self.own_copy:
+            self.host[:self.npre].copy_(self.dev[:self.npre], non_blocking=True)
 
     def collect(self, dtype) -> dict:
         """after the stream has been synchronised: {env index: terminal observation}"""
@@ -105,11 +120,15 @@ class _TerminalRows:
         if cnt == 0:
             return {}
         need = 4 + cnt * (self.d + 1)
-        if need > self.npre:
-            self.host[self.npre:need].copy_(self.dev[self.npre:need], non_blocking=True)
+        src_np, src_i = self.host_np, self.host_i
+        if need > self.npre:                             # more finished environments than the prefix holds (rare)
+            full = torch.zeros(need, dtype=torch.float32).pin_memory()
+            full.copy_(self.dev[:need], non_blocking=True)
             torch.cuda.current_stream(self.device).synchronize()
-        rec = self.host_np[4:need].reshape(cnt, self.d + 1)
-        idx = self.host_i[4:need].reshape(cnt, self.d + 1)[:, 0]
+            src_np = full.numpy()
+            src_i = src_np.view(np.int32)
+        rec = src_np[4:need].reshape(cnt, self.d + 1)
+        idx = src_i[4:need].reshape(cnt, self.d + 1)[:, 0]
         rows = rec[:, 1:].astype(dtype)                  # one copy = fresh memory for all terminal observations
         return {int(i): {"terminal_observation": rows[k]} for k, i in enumerate(idx.tolist())}
 
@@ -198,6 +217,9 @@ class B200MimicVecEnv:
             c.mirror_act_idx[i], c.mirror_act_sign[i] = int(ai[i]), float(asn[i])
         c.lanes_per_env = lanes_per_env
         c.early_termination = int(bool(cfg.early_termination))
+        hist_bytes = 4 * self.num_envs * max(1, cfg.ep_dur_max)
+        self._median_torque = bool(getattr(cfg, "median_torque", True)) and hist_bytes <= (1 << 30)
+        c.monitor_median_torque = int(self._median_torque)
         return c
 
     def _upload_mocap(self):
@@ -374,6 +396,15 @@ class B200MimicVecEnv:
         if attr_name in cabi.EXTRA_NAMES:
             col = cabi.EXTRA_NAMES.index(attr_name)
             vals = self.extras()[:, col].cpu().numpy()
+            return [float(vals[i]) for i in idx]
+        if attr_name == "median_abs_torque_smoothed":      # monitor_wrapper.py:131
+            if not self._median_torque:
+                raise AttributeError("median_abs_torque_smoothed: the env was built with EnvConfig(median_torque=False)")
+            with torch.cuda.device(self.device):
+                out = torch.zeros(self.num_envs, device=self.device)
+                lib.check(self._lib.drl_get_median_torque(self._handle, _ptr(out), self._stream()),
+                          "drl_get_median_torque")
+            vals = out.cpu().numpy()
             return [float(vals[i]) for i in idx]
         if attr_name == "ep_lens":
             # the reference returns one list per env and the callback flattens them (callback.py:227-230)
@@ -563,8 +594,15 @@ class B200VecNormalize:
         self._packed = [torch.zeros(2 * D + 3, dtype=torch.float64, device=dev) for _ in range(2)]
         self._packed_reset = torch.zeros(2 * D + 3, dtype=torch.float64, device=dev)
         self.ret = torch.zeros(self.num_envs, device=dev)
-        self._nobs = [torch.zeros(self.num_envs, D, device=dev) for _ in range(2)]
-        self._nrew = [torch.zeros(self.num_envs, device=dev) for _ in range(2)]
+        # normalised outputs of a step live side by side in one "pack" per buffer set - obs | rew | done | terminal
+        # records - so that the numpy API fetches a whole step with ONE device-to-host copy
+        N = self.num_envs
+        self._w_obs, self._w_rew, self._w_done = N * D, N, (N + 3) // 4
+        self._w_head = self._w_obs + self._w_rew + self._w_done
+        self._pack = [torch.zeros(self._w_head + _TerminalRows.words_for(N, D), device=dev) for _ in range(2)]
+        self._nobs = [p[:self._w_obs].view(N, D) for p in self._pack]
+        self._nrew = [p[self._w_obs:self._w_obs + N] for p in self._pack]
+        self._ndone = [p[self._w_obs + N:self._w_head].view(torch.uint8)[:N] for p in self._pack]
         self._k = 0
         # the normalisation kernel runs on a side stream so that it can overlap the next env step when the caller does
         # not consume the normalised tensors immediately
@@ -695,8 +733,9 @@ class B200VecNormalize:
             src, dst = self._rms[self._cur], self._rms[1 - self._cur]
             lib.check(self._lib.drl_vecnorm_step(_ptr(obs), _ptr(nobs), _ptr(rew), _ptr(nrew) if rew is not None else None,
                                                  self.num_envs, self._D, _ptr(packed), _ptr(src), _ptr(dst),
-                                                 _ptr(self.ret), _ptr(done), float(self.clip_obs),
-                                                 float(self.clip_reward), float(self.epsilon), flags, self._comm,
+                                                 _ptr(self.ret), _ptr(done), _ptr(self._ndone[k]),
+                                                 float(self.clip_obs), float(self.clip_reward), float(self.epsilon),
+                                                 flags, self._comm,
                                                  int(sync_every), C.c_void_p(stream.cuda_stream)), "drl_vecnorm_step")
             self.launches += 1
             self._calls += 1
@@ -761,20 +800,25 @@ class B200VecNormalize:
     def _host_buffers(self):
         if not hasattr(self, "_h"):
             N, D, A = self.num_envs, self._D, self.venv.act_dim
-            self._h = dict(act=torch.zeros(N, A).pin_memory(),
-                           obs=[torch.zeros(N, D).pin_memory() for _ in range(2)],
-                           rew=torch.zeros(N).pin_memory(), done=torch.zeros(N, dtype=torch.uint8).pin_memory())
-            self._h_np = dict(act=self._h["act"].numpy(), obs=[t.numpy() for t in self._h["obs"]],
-                              rew=self._h["rew"].numpy(), done=self._h["done"].numpy())
+            n_copy = self._w_head + _TerminalRows.prefix_words(N, D)
+            self._n_copy = n_copy
+            hp = [torch.zeros(n_copy).pin_memory() for _ in range(2)]            # two alternating host packs
+            self._h = dict(act=torch.zeros(N, A).pin_memory(), pack=hp)
+            self._h_np = dict(act=self._h["act"].numpy(),
+                              obs=[p[:self._w_obs].view(N, D).numpy() for p in hp],
+                              rew=[p[self._w_obs:self._w_obs + N].numpy() for p in hp],
+                              done=[p[self._w_obs + N:self._w_head].view(torch.uint8)[:N].numpy() for p in hp])
             self._hk = 0
             self._d_act = torch.zeros(N, A, device=self.device)
-            self._trows = _TerminalRows(N, D, self.device)
+            self._trows = [_TerminalRows(N, D, self.device, dev_words=self._pack[k][self._w_head:],
+                                         host_words=hp[0][self._w_head:]) for k in range(2)]
         return self._h
 
     def reset(self, inject=None):
         h = self._host_buffers()
         self._hk ^= 1
-        h["obs"][self._hk].copy_(self.reset_tensor(inject), non_blocking=True)
+        nobs = self.reset_tensor(inject)
+        h["pack"][self._hk][:self._w_obs].copy_(nobs.reshape(-1), non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()
         o = self._h_np["obs"][self._hk]
         return o.copy() if self.copy_outputs else o
@@ -788,15 +832,17 @@ class B200VecNormalize:
         h = self._h
         self._d_act.copy_(h["act"], non_blocking=True)
         obs, rew, done = self.step_tensor(self._d_act, inject)
+        k = self._k
         self._hk ^= 1
-        h["obs"][self._hk].copy_(obs, non_blocking=True)
-        h["rew"].copy_(rew, non_blocking=True)
-        h["done"].copy_(done, non_blocking=True)
         with torch.cuda.device(self.device):
-            # terminal observations normalised with the statistics just merged (SB3 VecNormalize.step_wait)
-            self._trows.enqueue(self._lib, self.venv.terminal_obs, done, self._rms[self._cur], self.clip_obs,
-                                self.epsilon, self.norm_obs, self.venv._stream())
+            # terminal observations normalised with the statistics just merged (SB3 VecNormalize.step_wait), compacted
+            # into the tail of this step's output pack
+            self._trows[k].enqueue(self._lib, self.venv.terminal_obs, done, self._rms[self._cur], self.clip_obs,
+                                   self.epsilon, self.norm_obs, self.venv._stream())
         self.launches += 1
+        # obs | rew | done | terminal-record prefix: one copy
+        h["pack"][self._hk].copy_(self._pack[k][:self._n_copy], non_blocking=True)
+        self._last = (k, self._hk)
 
     def _graph_key(self):
         v = self.venv
@@ -838,6 +884,7 @@ class B200VecNormalize:
         g, after, dl = entry
         g.replay()
         v._cur, self._k, self._cur, self._hk = after
+        self._last = (self._k, self._hk)
         self._calls += 1
         v.launches += dl[0]
         self.launches += dl[1]
@@ -852,13 +899,16 @@ class B200VecNormalize:
     def step_wait(self):
         hn = self._h_np
         torch.cuda.current_stream(self.device).synchronize()
-        done = hn["done"].astype(bool)
-        infos = LazyInfos(self.num_envs, self._trows.collect(np.float32))
+        k, hk = self._last
+        done = hn["done"][hk].astype(bool)
+        tr = self._trows[k]
+        tr.set_host(self._h["pack"][hk][self._w_head:])
+        infos = LazyInfos(self.num_envs, tr.collect(np.float32))
         if self.copy_outputs:
-            obs = self._h["obs"][self._hk].clone().numpy()          # multi-threaded copy out of the pinned buffer
+            obs = self._h["pack"][hk][:self._w_obs].view(self.num_envs, self._D).clone().numpy()   # multi-threaded copy
         else:
-            obs = hn["obs"][self._hk]
-        return obs, hn["rew"].copy(), done, infos
+            obs = hn["obs"][hk]
+        return obs, hn["rew"][hk].copy(), done, infos
 
     def step(self, actions, inject=None):
         self.step_async(actions, inject)
@@ -870,7 +920,7 @@ class B200VecNormalize:
     def d2h_bytes_per_step(self) -> int:
         """obs + reward + done + the terminal-record prefix (more only when > _TerminalRows.PREFIX envs finish)"""
         self._host_buffers()
-        return self.num_envs * (self._D * 4 + 4 + 1) + self._trows.npre * 4
+        return self._n_copy * 4
 
     def normalize_obs(self, obs: torch.Tensor) -> torch.Tensor:
         if not self.norm_obs:

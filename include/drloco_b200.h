@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define DRL_ABI_VERSION 1
+#define DRL_ABI_VERSION 2
 
 #define DRL_MAX_DOF 24
 #define DRL_MAX_BODY 12
@@ -116,6 +116,9 @@ typedef struct {
                                   * but never lets it end an episode (mimic_env.py:120-123): 0 = same here, the three
                                   * reasons are only counted (DRL_STAT_ET_*); 1 = a firing check also sets done (the
                                   * terminal reward is then -0.0 like a fall). */
+  int32_t monitor_median_torque; /* 1 = keep every env's per-episode history of the mean |actuator torque| (4 * ep_dur_max
+                                  * bytes per env) so that Monitor.median_abs_torque_smoothed (monitor_wrapper.py:131) can
+                                  * be served (drl_get_median_torque); 0 = skip it */
 } DrlConfig;
 
 typedef struct DrlEnv DrlEnv;    /* opaque: persistent per-env state, mocap tables, RNG counters */
@@ -212,6 +215,11 @@ int drl_get_episode_positions(DrlEnv* env, int32_t* rsi_pos, int32_t* et_pos, ui
  * -1 while that episode has not stepped yet. */
 int drl_get_running_rsi_positions(DrlEnv* env, int32_t* rsi_pos, void* stream);
 
+/* Monitor.median_abs_torque_smoothed (monitor_wrapper.py:131) of every env: the median over the finished episode of
+ * the per-step mean |actuator torque|, exponentially smoothed (0.75) at every episode end.  out: device float [N].
+ * DRL_ERR_STATE when the env was created with monitor_median_torque == 0. */
+int drl_get_median_torque(DrlEnv* env, float* out, void* stream);
+
 /* MimicEnv.activate_evaluation (mimic_env.py:245): deterministic init states (straight_walk_trajecs.py:237-265) */
 int drl_set_eval_mode(DrlEnv* env, int32_t on);
 
@@ -270,7 +278,8 @@ int drl_vecnorm_apply(const float* obs_in, float* obs_out, const float* rew_in, 
  * drl_vecnorm_step: exchange (peer stores into the mailboxes over NVLink + flags, summed in rank order: identical bits
  *   on every rank) + Chan merge into rms (rms_in -> rms_out, must not alias) + normalisation of obs / rew +
  *   ret[done] = 0.  flags: bit0 update the observation statistics, bit1 norm_obs, bit2 norm_reward, bit3 update the
- *   return statistics.  packed == NULL or no update bit: normalise only.  sync_every = K >= 1: a "cycle" call - the
+ *   return statistics.  packed == NULL or no update bit: normalise only.  done_out (nullable): a copy of `done`
+ *   next to the normalised outputs, so that one device-to-host copy can fetch a whole step.  sync_every = K >= 1: a "cycle" call - the
  *   moments are accumulated locally and exchanged / merged on every K-th cycle call (K = 1: every call, SB3's
  *   semantics; K > 1 is an opt-in amortisation); sync_every = 0: an "immediate" call - exchange and merge `packed` now,
  *   leaving the cycle alone (VecNormalize.reset).  All ranks must make the same sequence of calls.  Asynchronous on `stream`; CUDA-graph capturable (the step counter lives on
@@ -283,8 +292,8 @@ int drl_comm_connect(DrlComm* comm, const void* handles);
 int drl_comm_destroy(DrlComm* comm);
 int drl_vecnorm_step(const float* obs_in, float* obs_out, const float* rew_in, float* rew_out, int32_t n, int32_t d,
                      const double* packed, const double* rms_in, double* rms_out, float* ret, const uint8_t* done,
-                     float clip_obs, float clip_rew, float eps, int32_t flags, DrlComm* comm, int32_t sync_every,
-                     void* stream);
+                     uint8_t* done_out, float clip_obs, float clip_rew, float eps, int32_t flags, DrlComm* comm,
+                     int32_t sync_every, void* stream);
 
 /* rows of tobs_in whose done byte is set, normalised with rms ({mean[d], var[d], ...}) into tobs_out: the
  * infos[i]["terminal_observation"] VecNormalize returns (SB3 VecNormalize.step_wait). Other rows are left untouched. */

@@ -315,6 +315,7 @@ class OracleMonitor:
         self.ep_len_smoothed = self.ep_ret_smoothed = self.mean_reward_smoothed = 0
         self.mean_ep_pos_rew_smoothed = self.mean_ep_vel_rew_smoothed = self.mean_ep_com_rew_smoothed = 0
         self.mean_abs_ep_torque_smoothed = 0
+        self.median_abs_torque_smoothed = 0
         self.moved_distance = 0
 
     def _smooth(self, label, new_value, smoothing_factor=0.9):   # utils.py:312-329
@@ -355,6 +356,7 @@ class OracleMonitor:
             self.ep_len = 0
             self.moved_distance = self.env.walked_distance
             self.mean_abs_ep_torque_smoothed = self._smooth("mean_ep_tor", float(np.mean(self.ep_torques_abs)), 0.75)
+            self.median_abs_torque_smoothed = self._smooth("med_ep_tor", float(np.median(self.ep_torques_abs)), 0.75)
             self.ep_torques_abs = []
         return obs, reward, done, info
 

@@ -324,7 +324,7 @@ def test_env_logic_and_monitor_on_injected_states():
     # Monitor attributes served through get_attr (callback.py:106-108,142,162-164)
     for name in ("ep_len_smoothed", "ep_ret_smoothed", "mean_reward_smoothed", "mean_ep_pos_rew_smoothed",
                  "mean_ep_vel_rew_smoothed", "mean_ep_com_rew_smoothed", "moved_distance",
-                 "mean_abs_ep_torque_smoothed"):
+                 "mean_abs_ep_torque_smoothed", "median_abs_torque_smoothed"):
         got = np.array(env.get_attr(name))
         want = np.array([float(getattr(m, name)) for m in ora.envs])
         np.testing.assert_allclose(got, want, rtol=2e-4, atol=2e-5, err_msg=name)

@@ -83,7 +83,7 @@ def test_rollout_matches_reference(golden_dir, fixture, ep_dur_max):
             np.testing.assert_array_equal([m.env.et_flags for m in venv.envs], g["et"][t].astype(bool), err_msg=f"t={t}")
     for name in ("ep_len_smoothed", "ep_ret_smoothed", "mean_reward_smoothed", "moved_distance",
                  "mean_ep_pos_rew_smoothed", "mean_ep_vel_rew_smoothed", "mean_ep_com_rew_smoothed",
-                 "mean_abs_ep_torque_smoothed"):
+                 "mean_abs_ep_torque_smoothed", "median_abs_torque_smoothed"):
         got = np.array([float(getattr(m, name)) for m in venv.envs])
         np.testing.assert_allclose(got, g["mon_" + name], rtol=1e-12, atol=0, err_msg=name)
     np.testing.assert_array_equal([x for m in venv.envs for x in m.ep_lens], g["mon_ep_lens_flat"])
@@ -124,7 +124,7 @@ def test_w165_rollout_matches_reference(golden_dir):
     assert wraps >= 2 and g["done"].sum() >= 5             # the fixture crosses the end of the recording and has resets
     for name in ("ep_len_smoothed", "ep_ret_smoothed", "mean_reward_smoothed", "moved_distance",
                  "mean_ep_pos_rew_smoothed", "mean_ep_vel_rew_smoothed", "mean_ep_com_rew_smoothed",
-                 "mean_abs_ep_torque_smoothed"):
+                 "mean_abs_ep_torque_smoothed", "median_abs_torque_smoothed"):
         got = np.array([float(getattr(m, name)) for m in venv.envs])
         np.testing.assert_allclose(got, g["mon_" + name], rtol=1e-12, atol=0, err_msg=name)
     np.testing.assert_array_equal([x for m in venv.envs for x in m.ep_lens], g["mon_ep_lens_flat"])
@@ -191,7 +191,7 @@ def test_blowup_path_matches_reference(spec, golden_dir):
     np.testing.assert_array_equal([x for m in mons for x in m.ep_lens], g["mon_ep_lens_flat"])
     np.testing.assert_array_equal([x for m in mons for x in m.et_positions], g["mon_et_positions"])
     for name in ("ep_len_smoothed", "ep_ret_smoothed", "moved_distance", "mean_ep_pos_rew_smoothed",
-                 "mean_abs_ep_torque_smoothed"):
+                 "mean_abs_ep_torque_smoothed", "median_abs_torque_smoothed"):
         got = np.array([float(getattr(m, name)) for m in mons])
         np.testing.assert_allclose(got, g["mon_" + name], rtol=1e-12, err_msg=name)
     # env 1 had a one-step episode (two blow-ups in a row): the reference's np.mean of an empty list turns its

@@ -152,7 +152,7 @@ def gen_w165_rollout(n_envs=6, n_steps=160, seed=0, out="w165_rollout.npz"):
             g["obs"][t, i] = o
     for name in ("ep_len_smoothed", "ep_ret_smoothed", "mean_reward_smoothed", "moved_distance",
                  "mean_ep_pos_rew_smoothed", "mean_ep_vel_rew_smoothed", "mean_ep_com_rew_smoothed",
-                 "mean_abs_ep_torque_smoothed"):
+                 "mean_abs_ep_torque_smoothed", "median_abs_torque_smoothed"):
         g["mon_" + name] = np.array([float(getattr(m, name)) for m in envs])
     g["mon_ep_lens_flat"] = np.array([x for m in envs for x in m.ep_lens], np.int32)
     g["meta"] = np.array("reference MimicWalker165cm65kgEnv+Monitor (ENV_ID and mirroring set in the config as the "
@@ -235,7 +235,7 @@ def gen_w3d_rollout(n_envs=8, n_steps=400, seed=0, out="w3d_rollout.npz", hypers
     # Monitor attributes the callback reads through get_attr (callback.py:106-108,142,162-164,227)
     for name in ("ep_len_smoothed", "ep_ret_smoothed", "mean_reward_smoothed", "moved_distance",
                  "mean_ep_pos_rew_smoothed", "mean_ep_vel_rew_smoothed", "mean_ep_com_rew_smoothed",
-                 "mean_abs_ep_torque_smoothed"):
+                 "mean_abs_ep_torque_smoothed", "median_abs_torque_smoothed"):
         g["mon_" + name] = np.array([float(getattr(m, name)) for m in envs])
     g["mon_ep_lens"] = np.array([len(m.ep_lens) for m in envs], np.int32)
     g["mon_ep_lens_flat"] = np.array([x for m in envs for x in m.ep_lens], np.int32)
@@ -342,7 +342,7 @@ def gen_w3d_blowup(out="w3d_blowup.npz", n_envs=2, n_steps=30):
             g["qpos"][t, i] = e.sim.data.qpos
             g["cursor"][t, i] = (e.refs._i_step, e.refs._pos, e.refs.count_steps_same_vel, e.ep_dur)
     for name in ("ep_len_smoothed", "ep_ret_smoothed", "mean_reward_smoothed", "moved_distance",
-                 "mean_ep_pos_rew_smoothed", "mean_abs_ep_torque_smoothed"):
+                 "mean_ep_pos_rew_smoothed", "mean_abs_ep_torque_smoothed", "median_abs_torque_smoothed"):
         g["mon_" + name] = np.array([float(getattr(m, name)) for m in envs])
     g["mon_ep_lens_flat"] = np.array([x for m in envs for x in m.ep_lens], np.int32)
     g["mon_et_positions"] = np.array([x for m in envs for x in m.et_positions], np.int32)

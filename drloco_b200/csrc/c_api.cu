@@ -14,8 +14,8 @@
 #include "dev_model.h"
 
 namespace drl {
-size_t step_smem_bytes(int G, int envs_per_block, int fdv);
-cudaError_t launch_step(const StepArgs& a, int nv, int G, int rk4, int reset_only, int block, bool debug, int fdv,
+size_t step_smem_bytes(int G, int envs_per_block);
+cudaError_t launch_step(const StepArgs& a, int nv, int G, int rk4, int reset_only, int block, bool debug,
                         cudaStream_t st);
 cudaError_t launch_running_rsi(const int* state_i, int* out, int n, cudaStream_t st);
 bool topology_matches(int nv, int nb, const int* body_parent, const int* dof_body, const int* dof_type);
@@ -83,9 +83,8 @@ struct DrlEnv {
   int playback = 0;
   int frame_skip_override = -1;
   float* debug = nullptr;
-  // developer hooks (environment variables read at drl_create): generation of the dynamics evaluation (2 = fd_v2.cuh,
-  // 1 = fd_v1.cuh) and the per-evaluation CTA barrier; A/B runs of kernel variants without rebuilding
-  int fd_version = 2;
+  // developer hook (environment variable read at drl_create): placement of the per-evaluation CTA barrier, for A/B runs
+  // without rebuilding
   int stage_barrier = 1;
   float* tor_hist = nullptr;
   float* med_tor_sm = nullptr;
@@ -119,7 +118,6 @@ extern "C" int drl_create(const DrlConfig* cfg, DrlEnv** out) {
   if (cfg->device < 0 || cfg->device >= ndev) return fail(DRL_ERR_INVALID, "drl_create: no CUDA device %d", cfg->device);
   DrlEnv* e = new DrlEnv();
   e->cfg = *cfg;
-  e->fd_version = env_int("DRLOCO_B200_FD", 2) == 1 ? 1 : 2;
   e->stage_barrier = env_int("DRLOCO_B200_STAGE_BARRIER", 1);      // 0 none, 1 start of evaluation, 2 before the solver
   if (e->stage_barrier < 0 || e->stage_barrier > 2) e->stage_barrier = 1;
   *out = e;
@@ -195,15 +193,6 @@ static void free_state(DrlEnv* e) {
   }
 }
 
-static bool supports(const DrlWalkerModel* m, int j, int b) {
-  const int jb = m->dof_body[j];
-  while (b >= 0) {
-    if (b == jb) return true;
-    b = m->body_parent[b];
-  }
-  return false;
-}
-
 extern "C" int drl_upload_model(DrlEnv* e, const DrlWalkerModel* m) {
   if (!e || !m) return fail(DRL_ERR_INVALID, "drl_upload_model: null argument");
   const DrlConfig& c = e->cfg;
@@ -227,13 +216,10 @@ extern "C" int drl_upload_model(DrlEnv* e, const DrlWalkerModel* m) {
   d.imp_inv_width = 1.f / d.imp_width; d.imp_inv_mid = 1.f / d.imp_mid; d.imp_inv_1mmid = 1.f / (1.f - d.imp_mid);
   if (m->body_parent[0] != -1) return fail(DRL_ERR_INVALID, "model: body 0 must be the root");
   d.root_z0 = (float)m->body_pos[0][2];
-  int depth[kMaxBody];
   for (int b = 0; b < m->nb; b++) {
     const int p = m->body_parent[b];
     if (p >= b) return fail(DRL_ERR_INVALID, "model: bodies must be topologically ordered");
     if (b > 0 && p < 0) return fail(DRL_ERR_INVALID, "model: exactly one root body is supported");
-    depth[b] = p < 0 ? 0 : depth[p] + 1;
-    if (depth[b] >= kMaxLevel) return fail(DRL_ERR_INVALID, "model: tree too deep");
     d.body_parent[b] = p;
     d.body_mass[b] = (float)m->body_mass[b];
     d.body_invw_tran[b] = (float)m->body_invweight0[b][0];
@@ -242,30 +228,18 @@ extern "C" int drl_upload_model(DrlEnv* e, const DrlWalkerModel* m) {
       d.body_ipos[b][i] = (float)m->body_ipos[b][i];
       d.body_inertia[b][i] = (float)m->body_inertia[b][i];
     }
-    d.body_dof0[b] = -1; d.body_ndof[b] = 0;
-    int lv = depth[b];
-    if (lv + 1 > d.nlevel) d.nlevel = lv + 1;
-    d.level_body[lv][d.level_count[lv]++] = b;
   }
   int G = m->nv <= 16 ? 16 : 32;
   if (c.lanes_per_env != 0 && c.lanes_per_env != G)
     return fail(DRL_ERR_INVALID, "config: lanes_per_env must be 0 or %d for this model", G);
-  for (int lv = 0; lv < d.nlevel; lv++)
-    if (d.level_count[lv] * 3 > G) return fail(DRL_ERR_UNSUPPORTED, "model: too many bodies on one tree level");
-  for (int b = 0; b < m->nb; b++)
-    for (int b2 = 0; b2 < m->nb; b2++) {   // subtree membership
-      int x = b2;
-      while (x >= 0 && x != b) x = m->body_parent[x];
-      if (x == b) d.body_sub[b] |= 1u << b2;
-    }
   bool seen_hinge_root = false;
+  int body_ndof[kMaxBody] = {0};
   for (int j = 0; j < m->nv; j++) {
     const int b = m->dof_body[j];
     if (b < 0 || b >= m->nb) return fail(DRL_ERR_INVALID, "model: dof %d has a bad body", j);
     if (j > 0 && b < m->dof_body[j - 1]) return fail(DRL_ERR_INVALID, "model: dofs must be ordered by body");
-    if (d.body_dof0[b] < 0) d.body_dof0[b] = j;
-    d.body_ndof[b]++;
-    d.dof_body[j] = b; d.dof_type[j] = m->dof_type[j]; d.dof_axis[j] = m->dof_axis_idx[j];
+    body_ndof[b]++;
+    d.dof_body[j] = b; d.dof_type[j] = m->dof_type[j];
     d.dof_limited[j] = m->dof_limited[j];
     d.dof_code[j] = m->dof_axis_idx[j] | (m->dof_axis_sign[j] < 0 ? 4 : 0);
     d.dof_sign[j] = (float)m->dof_axis_sign[j]; d.dof_ref[j] = (float)m->dof_ref[j];
@@ -281,27 +255,12 @@ extern "C" int drl_upload_model(DrlEnv* e, const DrlWalkerModel* m) {
       seen_hinge_root = true;
     }
   }
-  if (e->fd_version == 2 && !topology_matches(m->nv, m->nb, d.body_parent, d.dof_body, d.dof_type))
+  // the tree itself (which body hangs where, which dofs move it) is compiled into the kernels as chain tables
+  if (!topology_matches(m->nv, m->nb, d.body_parent, d.dof_body, d.dof_type))
     return fail(DRL_ERR_UNSUPPORTED, "model: the kernels are compiled for the chain layout of walker3d_flat_feet.xml "
                                      "(nv 14) and walker_165cm_65kg.xml (nv 19); this model's tree differs");
-  for (int b = 0; b < m->nb; b++) {
-    if (d.body_ndof[b] == 0) return fail(DRL_ERR_UNSUPPORTED, "model: every body needs at least one joint");
-    d.body_hinge0[b] = d.body_dof0[b] + (b == 0 ? d.nslide : 0);
-  }
-  for (int j = 0; j < m->nv; j++) {
-    const int b = m->dof_body[j];
-    d.dof_last[j] = (j == d.body_dof0[b] + d.body_ndof[b] - 1) ? 1 : 0;
-    d.dof_subbodies[j] = d.body_sub[b];
-    for (int i = 0; i < m->nv; i++) {
-      if (i < j && supports(m, i, b)) d.dof_anc[j] |= 1u << i;
-    }
-  }
-  for (int j = 0; j < m->nv; j++)
-    for (int r = 0; r < m->nv; r++)
-      if ((d.dof_anc[r] >> j) & 1u) d.dof_desc[j] |= 1u << r;
   for (int b = 0; b < m->nb; b++)
-    for (int j = 0; j < m->nv; j++)
-      if (supports(m, j, b)) d.body_supp[b] |= 1u << j;
+    if (body_ndof[b] == 0) return fail(DRL_ERR_UNSUPPORTED, "model: every body needs at least one joint");
   for (int u = 0; u < m->nu; u++) {
     d.act_dof[u] = m->act_dof[u]; d.act_gear[u] = (float)m->act_gear[u];
     d.act_clo[u] = (float)m->act_ctrlrange[u][0]; d.act_chi[u] = (float)m->act_ctrlrange[u][1];
@@ -499,7 +458,7 @@ extern "C" int drl_reset(DrlEnv* e, const uint8_t* mask, const int32_t* inj_iste
   StepArgs a = make_args(e);
   a.reset_mask = mask; a.inj_istep = inj_istep; a.inj_pos = inj_pos; a.obs = obs;
   a.debug = nullptr;
-  CUDA_TRY(launch_step(a, e->nv, e->G, e->cfg.integrator == DRL_INTEGRATOR_RK4, 1, e->block, false, e->fd_version, (cudaStream_t)stream));
+  CUDA_TRY(launch_step(a, e->nv, e->G, e->cfg.integrator == DRL_INTEGRATOR_RK4, 1, e->block, false, (cudaStream_t)stream));
   return DRL_OK;
 }
 
@@ -514,8 +473,7 @@ extern "C" int drl_step(DrlEnv* e, const float* actions, float* obs, float* rew,
   a.inj_istep = inj_istep; a.inj_pos = inj_pos;
     const bool rk4 = e->cfg.integrator == DRL_INTEGRATOR_RK4;
   if (e->debug && rk4) return fail(DRL_ERR_UNSUPPORTED, "drl_step: the dump variant exists for the Euler integrator only");
-  CUDA_TRY(launch_step(a, e->nv, e->G, rk4, 0, e->block, e->debug != nullptr, e->fd_version,
-                       (cudaStream_t)stream));
+  CUDA_TRY(launch_step(a, e->nv, e->G, rk4, 0, e->block, e->debug != nullptr, (cudaStream_t)stream));
   return DRL_OK;
 }
 
@@ -684,7 +642,7 @@ extern "C" int drl_launch_info(DrlEnv* e, int32_t* lanes_per_env, int32_t* block
   if (lanes_per_env) *lanes_per_env = e->G;
   if (block_threads) *block_threads = e->block;
   if (grid_blocks) *grid_blocks = (e->cfg.num_envs + epb - 1) / epb;
-  if (smem_bytes) *smem_bytes = (int)step_smem_bytes(e->G, epb, e->fd_version);
+  if (smem_bytes) *smem_bytes = (int)step_smem_bytes(e->G, epb);
   return DRL_OK;
 }
 

@@ -12,32 +12,25 @@ constexpr int kMaxDof = 32;
 constexpr int kMaxAct = 16;
 constexpr int kMaxCand = 64;     // contact candidates: 8 corners per box, 1 per capsule end
 constexpr int kMaxSite = 16;
-constexpr int kMaxLevel = 6;
 constexpr int kMaxObs = 64;
 
 // alignas(16): the step kernel stages this struct into shared memory in 16-byte chunks (sizeof must be a multiple of 16)
 struct alignas(16) DevModel {
   // sizes
-  int nv, nb, nu, ncand, nbox_cand, nsite, nlevel, nslide;
+  int nv, nb, nu, ncand, nbox_cand, nsite, nslide, pad_sz_;
   float timestep, gravity_z;
   float Kc, Bc;                      // 1/(dmax^2 tc^2 dr^2), 2/(dmax tc)  (solref)
   float imp_d0, imp_dmax, imp_width, imp_mid, imp_power;
   float imp_inv_width, imp_inv_mid, imp_inv_1mmid;   // reciprocals used by the power-2 impedance curve
   float root_z0;                     // body_pos[root].z
   // bodies
+  // (the tree topology itself is compiled into the kernels: Topo<NV> in fd_tree.cuh)
   int body_parent[kMaxBody];
-  int body_dof0[kMaxBody], body_ndof[kMaxBody], body_hinge0[kMaxBody];   // hinge0: first hinge dof of the body
-  unsigned body_supp[kMaxBody];      // dofs that move body b
-  unsigned body_sub[kMaxBody];       // bodies in the subtree rooted at b (including b)
   float body_pos[kMaxBody][3], body_ipos[kMaxBody][3], body_inertia[kMaxBody][3];
   float body_mass[kMaxBody], body_invw_tran[kMaxBody];
-  int level_count[kMaxLevel], level_body[kMaxLevel][kMaxBody];
   // dofs
-  int dof_body[kMaxDof], dof_type[kMaxDof], dof_axis[kMaxDof], dof_limited[kMaxDof], dof_last[kMaxDof];
+  int dof_body[kMaxDof], dof_type[kMaxDof], dof_limited[kMaxDof];
   int dof_code[kMaxDof];             // axis index | (axis sign < 0) << 2
-  unsigned dof_anc[kMaxDof];         // dofs strictly before j on j's chain
-  unsigned dof_desc[kMaxDof];        // dofs r > j with j in anc(r)
-  unsigned dof_subbodies[kMaxDof];   // = body_sub[dof_body[j]]
   float dof_sign[kMaxDof], dof_ref[kMaxDof], dof_damping[kMaxDof], dof_armature[kMaxDof];
   float dof_lo[kMaxDof], dof_hi[kMaxDof], dof_invw[kMaxDof], dof_slide_z[kMaxDof];
   // actuators

@@ -1,4 +1,4 @@
-// fd_common.cuh — helpers shared by the dynamics-evaluation variants of the step kernel (internal to libdrloco_b200).
+// fd_common.cuh — small device helpers of the step kernel (internal to libdrloco_b200).
 #pragma once
 #include <cuda_runtime.h>
 #include <math.h>
@@ -117,13 +117,8 @@ struct LaneConst {
   int l;               // lane within the env group
   unsigned emask;      // lanes of this lane's environment within the warp
   bool isdof, isbody;
-  int body, type, limited, last;
-  float sign, ref, damping, armature, lo, hi, invw;
-  unsigned anc, desc, subb;
-};
-
-struct Counters {
-  int evals, iters, capped;
+  int body, type;      // body and joint type (0 slide, 1 hinge) of this lane's dof; the other per-dof constants are
+                       // read from the model block in shared memory where they are used (keeps them out of registers)
 };
 
 // active set carried from one dynamics evaluation to the next (lane <-> contact candidate is a fixed mapping)
@@ -138,47 +133,7 @@ __device__ __forceinline__ constexpr int sym6(int i, int j) {
   return (i <= j) ? (i * 6 - (i * (i - 1)) / 2 + (j - i)) : (j * 6 - (j * (j - 1)) / 2 + (i - j));
 }
 
-// pop the two lowest set bits of a mask (i1 = i0 and second = false when only one is left): the chain loops below
-// consume two entries per trip so that their shared-memory loads are in flight together
-__device__ __forceinline__ void pop2(unsigned& mk, int& i0, int& i1, bool& second) {
-  i0 = __ffs(mk) - 1;
-  mk &= mk - 1;
-  second = mk != 0u;
-  i1 = second ? __ffs(mk) - 1 : i0;
-  mk &= mk - 1;
-}
-
 // does predicate p hold on any lane of this lane's environment?
 __device__ __forceinline__ bool env_any(bool p, unsigned emask) { return (__ballot_sync(kFull, p) & emask) != 0u; }
-
-// LDL^T solve with the symmetric matrix spread one column per lane: H[0..NV-1] = rows of this lane's column (full
-// column, both triangles), H[NV] = this lane's rhs entry.  Right-looking elimination; column k is left unscaled
-// (H[r][k] = l_rk d_k) so that each trailing update is one shuffle + one FMA.  Returns x for this lane's row.
-template <int NV, int G>
-__device__ __forceinline__ float ldl_solve_cols(float (&H)[NV + 1], int l) {
-  float invd = 0.f;
-#pragma unroll
-  for (int k = 0; k < NV; k++) {
-    const float dk = __shfl_sync(kFull, H[k], k, G);
-    const float inv = fast_rcp(fmaxf(dk, 1e-30f));
-    const float lck = H[k] * inv;          // lanes c > k: l_ck = H[c][k] / d_k (H is symmetric)
-    const bool upd = l > k;
-    if (l == k) invd = inv;
-#pragma unroll
-    for (int r = k + 1; r <= NV; r++) {
-      const float vr = __shfl_sync(kFull, H[r], k, G);     // H[r][k];  r == NV: forward-substituted rhs z_k
-      if (upd) H[r] = fmaf(-vr, lck, H[r]);
-    }
-  }
-  // x_c = (z_c - sum_{r>c} H[r][c] x_r) / d_c
-  float sacc = H[NV], x = 0.f;
-#pragma unroll
-  for (int k = NV - 1; k >= 0; k--) {
-    const float xk = __shfl_sync(kFull, sacc * invd, k, G);
-    if (l < k) sacc = fmaf(-H[k], xk, sacc);
-    if (l == k) x = xk;
-  }
-  return x;
-}
 
 }  // namespace drl

@@ -1,6 +1,6 @@
-// fd_v2.cuh — second-generation dynamics evaluation of the step kernel (one mj_forward per call; restated in
-// oracle/walker_physics.c).  Same mathematics and the same lane <-> dof / contact-candidate ownership as fd_v1.cuh, but
-// every tree recursion is laid out along the walker's kinematic CHAINS (root -> leg / root -> trunk), whose shape is a
+// fd_tree.cuh — the dynamics evaluation of the step kernel (one mj_forward per call; restated in
+// oracle/walker_physics.c).  Lane j of an environment owns dof j and one or two contact candidates; every tree
+// recursion is laid out along the walker's kinematic CHAINS (root -> leg / root -> trunk), whose shape is a
 // compile-time property of the two reference models (drloco/mujoco/xml/walker3d_flat_feet.xml, walker_165cm_65kg.xml):
 //
 //   * body frames: three "row lanes" per chain carry one row of the rotation matrix down the whole chain in registers
@@ -135,7 +135,7 @@ __device__ __forceinline__ float ldl_solve_tree(float (&H)[NV + 1], int l) {
 constexpr int kWredBox = 29;                         // entries reserved per box (27 used)
 
 template <int G>
-struct EnvSmem2 {
+struct EnvSmem {
   static constexpr int kWredHalf = (G == 16 ? 2 * kWredBox * 4 + 8 : 4 * kWredBox * 4);
   static_assert(kWredHalf % 32 == 16, "bank layout of the staging buffer");
   float v[G];               // qvel at the current stage
@@ -178,8 +178,8 @@ struct EnvSmem2 {
   // chain scans (six components per chain, chains 16 banks apart)
   float pad_[(G == 16) ? 20 : 4];
 };
-static_assert((sizeof(EnvSmem2<16>) / 4) % 32 == 8, "environment stride must be 8 mod 32 floats (bank layout)");
-static_assert(sizeof(EnvSmem2<16>) % 16 == 0 && sizeof(EnvSmem2<32>) % 16 == 0, "vector loads need 16-byte rows");
+static_assert((sizeof(EnvSmem<16>) / 4) % 32 == 8, "environment stride must be 8 mod 32 floats (bank layout)");
+static_assert(sizeof(EnvSmem<16>) % 16 == 0 && sizeof(EnvSmem<32>) % 16 == 0, "vector loads need 16-byte rows");
 
 // lane roles that depend on the chain layout (constant over the launch)
 struct ChainLane {
@@ -198,7 +198,7 @@ __device__ __forceinline__ void rot_row(int ax, float& R0, float& R1, float& R2,
 // Body frames relative to O and world joint axes for the joint configuration published in E.cssn (mj_kinematics for
 // hinges anchored at the body origin; the root slides move O itself).  Lane (chain, row) walks its chain once.
 template <int NV, int G>
-__device__ __forceinline__ void tree_kinematics2(const DevModel& M, EnvSmem2<G>& E, const ChainLane& C, int l) {
+__device__ __forceinline__ void tree_kinematics(const DevModel& M, EnvSmem<G>& E, const ChainLane& C, int l) {
   using T = Topo<NV>;
   if (l < 3 * T::NCHAIN) {
     const int c = C.c3, r = C.row;
@@ -232,7 +232,7 @@ __device__ __forceinline__ void tree_kinematics2(const DevModel& M, EnvSmem2<G>&
 
 // z of a point given in the frame of body b, relative to O
 template <int G>
-__device__ __forceinline__ float body_point_z(const EnvSmem2<G>& E, int b, const float* p) {
+__device__ __forceinline__ float body_point_z(const EnvSmem<G>& E, int b, const float* p) {
   const float4 r2 = *reinterpret_cast<const float4*>(&E.bodyR[b][8]);
   return r2.w + r2.x * p[0] + r2.y * p[1] + r2.z * p[2];
 }
@@ -240,7 +240,7 @@ __device__ __forceinline__ float body_point_z(const EnvSmem2<G>& E, int b, const
 // Prefix sum of coef[j] * S_j along chain c for spatial component `comp`.  PRE: store the value before each dof into
 // E.Fd[j]; body-end values go to dst[b][comp] (dst rows are 8 floats).
 template <int NV, int G, bool PRE>
-__device__ __forceinline__ void chain_prefix(EnvSmem2<G>& E, const float* coef, float (*dst)[8], int c, int comp,
+__device__ __forceinline__ void chain_prefix(EnvSmem<G>& E, const float* coef, float (*dst)[8], int c, int comp,
                                              float init) {
   using T = Topo<NV>;
   const int cd0 = T::chain_dof0(c), cb1 = T::chain_body1(c), clen = T::chain_len(c);
@@ -267,7 +267,7 @@ __device__ __forceinline__ void chain_prefix(EnvSmem2<G>& E, const float* coef, 
 // Sum of src rows [b][comp] (stride floats apart) into running totals along every chain without a product: used for
 // the bias accelerations, whose terms are already per dof (E.Fd rows).
 template <int NV, int G>
-__device__ __forceinline__ void chain_prefix_rows(EnvSmem2<G>& E, float (*dst)[8], int c, int comp, float init) {
+__device__ __forceinline__ void chain_prefix_rows(EnvSmem<G>& E, float (*dst)[8], int c, int comp, float init) {
   using T = Topo<NV>;
   const int cd0 = T::chain_dof0(c), cb1 = T::chain_body1(c), clen = T::chain_len(c);
   float acc = init;
@@ -323,7 +323,7 @@ __device__ __forceinline__ Contact ld_contact(const float* p) {
 
 // contact point, regulariser and reference accelerations of candidate s on body b at signed distance dist
 template <int G, bool BOX>
-__device__ __forceinline__ void contact_setup(const DevModel& M, const EnvSmem2<G>& E, int s, int b, float dist,
+__device__ __forceinline__ void contact_setup(const DevModel& M, const EnvSmem<G>& E, int s, int b, float dist,
                                               Contact& c) {
   const float4 r0 = *reinterpret_cast<const float4*>(&E.bodyR[b][0]);
   const float4 r1 = *reinterpret_cast<const float4*>(&E.bodyR[b][4]);
@@ -406,7 +406,7 @@ __device__ __forceinline__ unsigned contact_rows(const Contact& c, const Vec6& T
 // part above comes from the transposed entries through shared memory.  E.Mt aliases V/Ab/T/W/U: callers guarantee
 // those are dead.  Output in registers H[0..NV-1] (armature on the diagonal).
 template <int NV, int G>
-__device__ __forceinline__ void mass_column2(const DevModel& M, EnvSmem2<G>& E, const LaneConst& L, const Vec6& S,
+__device__ __forceinline__ void mass_column(const DevModel& M, EnvSmem<G>& E, const LaneConst& L, const Vec6& S,
                                              float (&H)[NV + 1]) {
   constexpr int kMs = (NV % 2 == 0) ? NV + 1 : NV + 2;
   static_assert(NV * kMs <= (int)(sizeof(E.Mt) / sizeof(float)), "Mt too small");
@@ -432,11 +432,11 @@ __device__ __forceinline__ void mass_column2(const DevModel& M, EnvSmem2<G>& E, 
 // between evaluations.  Must be called by all 32 lanes of the warp (warp-uniform control flow).  On return E.S holds the
 // motion vectors, E.Ic the composite inertias and E.acc the accelerations (used by the Euler damping solve).
 template <int NV, int G, bool DBG>
-__device__ __forceinline__ void forward_dynamics2(const DevModel& M, EnvSmem2<G>& E, const LaneConst& L,
+__device__ __forceinline__ void forward_dynamics(const DevModel& M, EnvSmem<G>& E, const LaneConst& L,
                                                   const ChainLane& C, float q, float v, float tau, float& a,
                                                   ActiveSet& AS, Vec6& S, float* dbg, bool solver_barrier) {
   using T = Topo<NV>;
-  using ES = EnvSmem2<G>;
+  using ES = EnvSmem<G>;
   const int l = L.l;
   const bool iscomp = l < 6 * T::NCHAIN;
   // ---- 1. joint trig + velocity ------------------------------------------------------------------------------------
@@ -451,7 +451,7 @@ __device__ __forceinline__ void forward_dynamics2(const DevModel& M, EnvSmem2<G>
 #pragma unroll
   for (int j = 0; j < T::NSLIDE; j++) zO = fmaf(M.dof_slide_z[j], E.cssn[j][1], zO);
   // ---- 2. body frames ----------------------------------------------------------------------------------------------
-  tree_kinematics2<NV, G>(M, E, C, l);
+  tree_kinematics<NV, G>(M, E, C, l);
   // ---- 3. motion vectors, body inertias about O ----------------------------------------------------------------------
   S = Vec6{0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   if (L.isdof) {
@@ -744,7 +744,7 @@ __device__ __forceinline__ void forward_dynamics2(const DevModel& M, EnvSmem2<G>
       st6(E.Fd[l], F);
     }
     __syncwarp();      // also: every lane is done with W / U before Mt (same storage) is written
-    mass_column2<NV, G>(M, E, L, S, H);
+    mass_column<NV, G>(M, E, L, S, H);
     if (AS.lbit) {
 #pragma unroll
       for (int r = 0; r < NV; r++)
@@ -799,14 +799,14 @@ __device__ __forceinline__ void forward_dynamics2(const DevModel& M, EnvSmem2<G>
 }
 
 // Column l of the plain joint-space inertia matrix (no contact terms) from the motion vectors and composite inertias
-// left behind by forward_dynamics2: the implicit-damping solve of the Euler integrator and the test dump use it.
+// left behind by forward_dynamics: the implicit-damping solve of the Euler integrator and the test dump use it.
 template <int NV, int G>
-__device__ __forceinline__ void pure_mass_column2(const DevModel& M, EnvSmem2<G>& E, const LaneConst& L,
+__device__ __forceinline__ void pure_mass_column(const DevModel& M, EnvSmem<G>& E, const LaneConst& L,
                                                   const Vec6& S, float (&H)[NV + 1]) {
   __syncwarp();
   if (L.isdof) st6(E.Fd[L.l], inertia_mul(E.Ic[L.body], S));
   __syncwarp();
-  mass_column2<NV, G>(M, E, L, S, H);
+  mass_column<NV, G>(M, E, L, S, H);
   __syncwarp();
 }
 

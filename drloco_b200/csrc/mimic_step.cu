@@ -12,8 +12,8 @@
 // Mapping: one environment per group of G lanes (G = 16 for nv <= 16: two environments per warp; G = 32 otherwise),
 // lane j owns dof j: its q/v/RK4 accumulators, its motion vector S_j and column j of the constraint Hessian live in
 // registers for the whole launch; per-env tree quantities (body frames, spatial inertias, velocities, contact
-// Hessians) live in shared memory; all frame_skip x 4 dynamics evaluations run inside the launch, HBM is touched once
-// on entry and once on exit.  Control flow is kept warp-uniform (the two environments of a warp run in lockstep, with
+// Hessians) live in shared memory and are produced by chain-ordered scans (fd_tree.cuh); all frame_skip x 4 dynamics
+// evaluations run inside the launch, HBM is touched once on entry and once on exit.  Control flow is kept warp-uniform (the two environments of a warp run in lockstep, with
 // predicated effects), so every shuffle / ballot / barrier uses the full-warp mask and compiles to a bare instruction.
 // Spatial quantities are expressed in world orientation about O = the root body origin (keeps fp32 cancellation
 // independent of how far the walker has travelled).
@@ -23,8 +23,7 @@
 // with W_b the 6x6 wrench-space Hessian of the active pyramid rows of all contacts on body b; primal active-set
 // iteration with full Newton steps, warm-started from the previous evaluation; LDL^T in registers via shuffles.
 #include "fd_common.cuh"
-#include "fd_v1.cuh"
-#include "fd_v2.cuh"
+#include "fd_tree.cuh"
 
 namespace drl {
 
@@ -208,25 +207,6 @@ __device__ __forceinline__ void write_obs(const DevModel& M, ES& E, int l, bool 
   __syncwarp();
 }
 
-// kinematics + foot-site height for either shared-memory layout
-template <int NV, int G>
-__device__ __forceinline__ void reset_kinematics(const DevModel& M, EnvSmem<G>& E, const ChainLane&, int l) {
-  tree_kinematics<G>(M, E, l);
-}
-template <int NV, int G>
-__device__ __forceinline__ void reset_kinematics(const DevModel& M, EnvSmem2<G>& E, const ChainLane& C, int l) {
-  tree_kinematics2<NV, G>(M, E, C, l);
-}
-template <int G>
-__device__ __forceinline__ float site_height(const EnvSmem<G>& E, int b, const float* p) {
-  const float* R = E.bodyR[b];
-  return R[11] + R[6] * p[0] + R[7] * p[1] + R[8] * p[2];
-}
-template <int G>
-__device__ __forceinline__ float site_height(const EnvSmem2<G>& E, int b, const float* p) {
-  return body_point_z<G>(E, b, p);
-}
-
 template <int NV, int G, class ES>
 __device__ __noinline__ void reset_env(const DevModel& M, const StepArgs& A, ES& E, const LaneConst& L,
                                        const ChainLane& CL, int env, Cursor& c, float& q, float& v, float& dist,
@@ -263,16 +243,17 @@ __device__ __noinline__ void reset_env(const DevModel& M, const StepArgs& A, ES&
   q = rq; v = rv;
   // set_state + sim.forward: lowest foot-corner site (mimic_env.py:546-559)
   {
-    float s = q - L.ref, cc = 1.f;
-    if (L.isdof && L.type == 1) sincosf(L.sign * (q - L.ref), &s, &cc);
+    const float ref = M.dof_ref[L.isdof ? l : 0];
+    float s = q - ref, cc = 1.f;
+    if (L.isdof && L.type == 1) sincos_joint(M.dof_sign[l] * (q - ref), s, cc);
     if (L.isdof) *reinterpret_cast<float2*>(&E.cssn[l][0]) = make_float2(cc, s);
   }
   __syncwarp();
   float zO = M.root_z0;
   for (int j = 0; j < M.nslide; j++) zO = fmaf(M.dof_slide_z[j], E.cssn[j][1], zO);
-  reset_kinematics<NV, G>(M, E, CL, l);
+  tree_kinematics<NV, G>(M, E, CL, l);
   float sz = 3.0e38f;
-  for (int s = l; s < M.nsite; s += G) sz = fminf(sz, zO + site_height<G>(E, M.site_body[s], M.site_pos[s]));
+  for (int s = l; s < M.nsite; s += G) sz = fminf(sz, zO + body_point_z<G>(E, M.site_body[s], M.site_pos[s]));
   const float lowest = group_min<G>(sz);
   if (l == M.com_z_dof) q -= lowest;
   zoff = lowest;                               // refs.adjust_COM_Z_pos(lowest)
@@ -280,14 +261,9 @@ __device__ __noinline__ void reset_env(const DevModel& M, const StepArgs& A, ES&
   __syncwarp();
 }
 
-template <int G, int FDV>
-struct SmemOf { using type = EnvSmem<G>; };
-template <int G>
-struct SmemOf<G, 2> { using type = EnvSmem2<G>; };
-
-template <int NV, int G, bool RK4, bool DBG, int FDV>
+template <int NV, int G, bool RK4, bool DBG>
 __global__ void __launch_bounds__(128, 4) mimic_step_kernel(const StepArgs A, const int do_reset_only) {
-  using ES = typename SmemOf<G, FDV>::type;
+  using ES = EnvSmem<G>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   DevModel& M = *reinterpret_cast<DevModel*>(smem_raw);
   constexpr int kModelBytes = (sizeof(DevModel) + 15) / 16 * 16;
@@ -317,10 +293,7 @@ __global__ void __launch_bounds__(128, 4) mimic_step_kernel(const StepArgs A, co
   L.isdof = l < M.nv;
   L.isbody = l < M.nb;
   const int jd = L.isdof ? l : 0;
-  L.body = M.dof_body[jd]; L.type = M.dof_type[jd]; L.limited = M.dof_limited[jd]; L.last = M.dof_last[jd];
-  L.sign = M.dof_sign[jd]; L.ref = M.dof_ref[jd]; L.damping = M.dof_damping[jd]; L.armature = M.dof_armature[jd];
-  L.lo = M.dof_lo[jd]; L.hi = M.dof_hi[jd]; L.invw = M.dof_invw[jd];
-  L.anc = M.dof_anc[jd]; L.desc = M.dof_desc[jd]; L.subb = M.dof_subbodies[jd];
+  L.body = M.dof_body[jd]; L.type = M.dof_type[jd];
 
   float* sf = A.state_f + (size_t)env * (4 * G);
   int* si = A.state_i + (size_t)env * kCurCount8;
@@ -329,10 +302,7 @@ __global__ void __launch_bounds__(128, 4) mimic_step_kernel(const StepArgs A, co
   c.i_step = si[kCurIstep]; c.pos = si[kCurPos]; c.count = si[kCurCount]; c.ep_dur = si[kCurEpDur];
   c.rsi_step = si[kCurRsiStep]; c.n_det = si[kCurNDet]; c.resets = si[kCurResets]; c.flags = si[kCurFlags];
   float dist = sf[3 * G + kMiscDist], zoff = sf[3 * G + kMiscZoff];
-  Counters cnt = {0, 0, 0};
-  if constexpr (FDV == 2) {
-    if (l == 0) { E.cnt[0] = 0; E.cnt[1] = 0; }
-  }
+  if (l == 0) { E.cnt[0] = 0; E.cnt[1] = 0; }
   // active set of the last evaluation of the previous step (bits 0-3 / 4-7: pyramid rows of the two candidates,
   // 8-9: candidates in contact, 10: limit row active, 11: limit violated)
   int* sa = A.state_as + (size_t)env * G;
@@ -413,12 +383,8 @@ __global__ void __launch_bounds__(128, 4) mimic_step_kernel(const StepArgs A, co
         // (the dynamics evaluation is ~80 KB of straight-line code); measured +3 %
         // (one barrier per substep instead of per stage loses the gain; a second barrier inside the evaluation adds none)
         if (A.stage_barrier == 1) __syncthreads();
-        if constexpr (FDV == 2) {
-          Vec6 Sj;
-          forward_dynamics2<NV, G, DBG>(M, E, L, CL, q, v, tau, a, AS, Sj, dbgp, A.stage_barrier == 2);
-        } else {
-          forward_dynamics<NV, G, DBG>(M, E, L, q, v, tau, a, AS, cnt, dbgp);
-        }
+        Vec6 Sj;
+        forward_dynamics<NV, G, DBG>(M, E, L, CL, q, v, tau, a, AS, Sj, dbgp, A.stage_barrier == 2);
         const float bw = (st == 0 || st == 3) ? (1.f / 6.f) : (1.f / 3.f);
         accq = fmaf(bw, v, accq);
         accv = fmaf(bw, a, accv);
@@ -435,29 +401,17 @@ __global__ void __launch_bounds__(128, 4) mimic_step_kernel(const StepArgs A, co
       // mj_Euler with implicit joint damping: (M + h B) a' = M a   [M a = tau_total + J'f]
       float Hc[NV + 1];
       float Ma = 0.f;
-      if constexpr (FDV == 2) {
-        Vec6 Sj;
-        forward_dynamics2<NV, G, DBG>(M, E, L, CL, q, v, tau, a, AS, Sj, dbgp, false);
-        pure_mass_column2<NV, G>(M, E, L, Sj, Hc);     // E.acc holds the constrained qacc of every dof
+      Vec6 Sj;
+      forward_dynamics<NV, G, DBG>(M, E, L, CL, q, v, tau, a, AS, Sj, dbgp, false);
+      pure_mass_column<NV, G>(M, E, L, Sj, Hc);     // E.acc holds the constrained qacc of every dof
 #pragma unroll
-        for (int r = 0; r < NV; r++) {
-          if (DBG && dbgp) dbgp[(2 + r) * 32 + l] = Hc[r];
-          Ma = fmaf(Hc[r], E.acc[r], Ma);
-          if (r == l) Hc[r] += h * L.damping;
-        }
-      } else {
-        forward_dynamics<NV, G, DBG>(M, E, L, q, v, tau, a, AS, cnt, dbgp);
-        __syncwarp();   // E.acc holds the constrained qacc of every dof
-        // E.Mc still holds this lane's column from the evaluation above
-#pragma unroll
-        for (int r = 0; r < NV; r++) {
-          const float m = E.Mc[r * G + l];
-          Ma = fmaf(m, E.acc[r], Ma);
-          Hc[r] = m + (r == l ? h * L.damping : 0.f);
-        }
+      for (int r = 0; r < NV; r++) {
+        if (DBG && dbgp) dbgp[(2 + r) * 32 + l] = Hc[r];
+        Ma = fmaf(Hc[r], E.acc[r], Ma);
+        if (r == l) Hc[r] += h * M.dof_damping[jd];
       }
       Hc[NV] = Ma;
-      float an = ldl_solve_cols<NV, G>(Hc, l);
+      float an = ldl_solve_tree<NV, G>(Hc, l);
       if (!L.isdof) an = 0.f;
       v = fmaf(h, an, v);
       q = fmaf(h, v, q);
@@ -568,15 +522,9 @@ __global__ void __launch_bounds__(128, 4) mimic_step_kernel(const StepArgs A, co
     srow[kRowStats + DRL_STAT_COM_REW_SUM] = (double)com_rew;
     srow[kRowStats + DRL_STAT_REW_STEPS] = 1.0;
     srow[kRowStats + DRL_STAT_ABS_TORQUE_SUM] = (double)mean_abs_torque;
-    if constexpr (FDV == 2) {
-      srow[kRowStats + DRL_STAT_SOLVER_ITERS] = (double)E.cnt[0];
-      srow[kRowStats + DRL_STAT_DYN_EVALS] = (double)(A.frame_skip * (RK4 ? 4 : 1));
-      srow[kRowStats + DRL_STAT_SOLVER_CAPPED] = (double)E.cnt[1];
-    } else {
-      srow[kRowStats + DRL_STAT_SOLVER_ITERS] = (double)cnt.iters;
-      srow[kRowStats + DRL_STAT_DYN_EVALS] = (double)cnt.evals;
-      srow[kRowStats + DRL_STAT_SOLVER_CAPPED] = (double)cnt.capped;
-    }
+    srow[kRowStats + DRL_STAT_SOLVER_ITERS] = (double)E.cnt[0];
+    srow[kRowStats + DRL_STAT_DYN_EVALS] = (double)(A.frame_skip * (RK4 ? 4 : 1));
+    srow[kRowStats + DRL_STAT_SOLVER_CAPPED] = (double)E.cnt[1];
     if (!bad) {
       srow[kRowStats + DRL_STAT_ET_COM_LOW] = et_low ? 1.0 : 0.0;
       srow[kRowStats + DRL_STAT_ET_TRUNK] = et_trunk ? 1.0 : 0.0;
@@ -778,21 +726,19 @@ __global__ void state_copy_kernel(float* state_f, int* state_i, int* state_as, f
 // ------------------------------------------------------------------------------------------------------------------
 // BASELINE.json configs[1] (4096 walker3d envs = 27.7 envs per SM) is one wave only if four 128-thread blocks fit an SM:
 // 4 x (model + 8 environments + 1 KB reserved) <= 228 KB
-static_assert(4 * ((sizeof(DevModel) + 15) / 16 * 16 + 8 * sizeof(EnvSmem2<16>) + 1024) <= 228 * 1024,
+static_assert(4 * ((sizeof(DevModel) + 15) / 16 * 16 + 8 * sizeof(EnvSmem<16>) + 1024) <= 228 * 1024,
               "walker3d: four blocks per SM must fit in shared memory");
 
-size_t step_smem_bytes(int G, int envs_per_block, int fdv) {
+size_t step_smem_bytes(int G, int envs_per_block) {
   const size_t model = (sizeof(DevModel) + 15) / 16 * 16;
-  const size_t per_env = fdv == 2 ? (G == 16 ? sizeof(EnvSmem2<16>) : sizeof(EnvSmem2<32>))
-                                  : (G == 16 ? sizeof(EnvSmem<16>) : sizeof(EnvSmem<32>));
-  return model + (size_t)envs_per_block * per_env;
+  return model + (size_t)envs_per_block * (G == 16 ? sizeof(EnvSmem<16>) : sizeof(EnvSmem<32>));
 }
 
-template <int NV, int G, bool RK4, bool DBG, int FDV>
+template <int NV, int G, bool RK4, bool DBG>
 static cudaError_t launch_one(const StepArgs& a, int reset_only, int block, cudaStream_t st) {
   const int epb = block / G;
-  const size_t smem = step_smem_bytes(G, epb, FDV);
-  auto kern = mimic_step_kernel<NV, G, RK4, DBG, FDV>;
+  const size_t smem = step_smem_bytes(G, epb);
+  auto kern = mimic_step_kernel<NV, G, RK4, DBG>;
   // function attributes are per device: set them once for every device this process launches on
   static unsigned long long attr_done = 0ull;
   int dev = 0;
@@ -811,29 +757,24 @@ static cudaError_t launch_one(const StepArgs& a, int reset_only, int block, cuda
   return cudaGetLastError();
 }
 
-template <int NV, int G, int FDV>
-static cudaError_t launch_fd(const StepArgs& a, int rk4, int reset_only, int block, bool debug, cudaStream_t st) {
-  if (rk4) return launch_one<NV, G, true, false, FDV>(a, reset_only, block, st);
-  return debug ? launch_one<NV, G, false, true, FDV>(a, reset_only, block, st)
-               : launch_one<NV, G, false, false, FDV>(a, reset_only, block, st);
+template <int NV, int G>
+static cudaError_t launch_model(const StepArgs& a, int rk4, int reset_only, int block, bool debug, cudaStream_t st) {
+  if (rk4) return launch_one<NV, G, true, false>(a, reset_only, block, st);
+  return debug ? launch_one<NV, G, false, true>(a, reset_only, block, st)
+               : launch_one<NV, G, false, false>(a, reset_only, block, st);
 }
 
-// instantiated: walker3d (nv 14, 16 lanes) and walker_165cm_65kg (nv 19, 32 lanes), RK4 and Euler, both generations of
-// the dynamics evaluation (fdv 2 = fd_v2.cuh, the default; 1 = fd_v1.cuh); the dump variant exists for the Euler
-// kernels only (tests evaluate single forward passes with it)
-cudaError_t launch_step(const StepArgs& a, int nv, int G, int rk4, int reset_only, int block, bool debug, int fdv,
+// instantiated: walker3d (nv 14, 16 lanes) and walker_165cm_65kg (nv 19, 32 lanes), RK4 and Euler; the dump variant
+// exists for the Euler kernels only (tests evaluate single forward passes with it)
+cudaError_t launch_step(const StepArgs& a, int nv, int G, int rk4, int reset_only, int block, bool debug,
                         cudaStream_t st) {
   if (debug && rk4) return cudaErrorInvalidValue;
-  if (nv == 14 && G == 16)
-    return fdv == 2 ? launch_fd<14, 16, 2>(a, rk4, reset_only, block, debug, st)
-                    : launch_fd<14, 16, 1>(a, rk4, reset_only, block, debug, st);
-  if (nv == 19 && G == 32)
-    return fdv == 2 ? launch_fd<19, 32, 2>(a, rk4, reset_only, block, debug, st)
-                    : launch_fd<19, 32, 1>(a, rk4, reset_only, block, debug, st);
+  if (nv == 14 && G == 16) return launch_model<14, 16>(a, rk4, reset_only, block, debug, st);
+  if (nv == 19 && G == 32) return launch_model<19, 32>(a, rk4, reset_only, block, debug, st);
   return cudaErrorInvalidValue;
 }
 
-// does the uploaded model have the chain shape the fd_v2 kernels are compiled for?  (host-side check, c_api.cu)
+// does the uploaded model have the chain shape the kernels are compiled for?  (host-side check, c_api.cu)
 template <int NV>
 static bool topo_ok(int nb, const int* body_parent, const int* dof_body, const int* dof_type) {
   using T = Topo<NV>;

@@ -13,6 +13,7 @@ Two ways to step:
 from __future__ import annotations
 
 import ctypes as C
+import os
 from collections.abc import Sequence
 from typing import Any, List, Optional, Tuple
 
@@ -218,7 +219,8 @@ class B200MimicVecEnv:
         c.lanes_per_env = lanes_per_env
         c.early_termination = int(bool(cfg.early_termination))
         hist_bytes = 4 * self.num_envs * max(1, cfg.ep_dur_max)
-        self._median_torque = bool(getattr(cfg, "median_torque", True)) and hist_bytes <= (1 << 30)
+        self._median_torque = bool(getattr(cfg, "median_torque", True)) and hist_bytes <= (1 << 30) \
+            and os.environ.get("DRLOCO_B200_MEDIAN_TORQUE", "1") != "0"          # developer hook for A/B timing
         c.monitor_median_torque = int(self._median_torque)
         return c
 

@@ -37,9 +37,10 @@ class EnvConfig:
     fall_z: float = 0.5                                 # mimic_env.py:120
     early_termination: bool = False                     # True: do_terminate_early (mimic_env.py:652-702) also ends the
                                                         # episode; the reference never does (mimic_env.py:120-123)
-    median_torque: bool = True                          # keep the per-episode torque history behind Monitor's
-                                                        # median_abs_torque_smoothed (4 * ep_dur_max bytes per env;
-                                                        # switched off automatically above 1 GiB)
+    median_torque: bool = False                         # True: keep the per-episode torque history behind Monitor's
+                                                        # median_abs_torque_smoothed (monitor_wrapper.py:131; 4 *
+                                                        # ep_dur_max bytes per env and a radix-select median at every
+                                                        # episode end).  The reference's callback never reads it.
     gamma: float = 0.0                                  # 0 -> by ctrl_freq, hypers.py:68
     integrator: str = "rk4"                             # xml:11; "euler" = MuJoCo semi-implicit Euler (fast mode)
     seed: int = 33                                      # utils.py:97

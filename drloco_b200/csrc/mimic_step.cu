@@ -107,30 +107,88 @@ __device__ __forceinline__ int group_sum_int(int x) {
   return x;
 }
 
-// np.median of the first n entries of hist (non-negative floats), computed by the G lanes of an environment with a
-// bitwise radix select (31 counting passes per order statistic).  Called by every lane of the warp; n may differ
-// between the two environments of a warp, n == 0 returns 0.  Runs once per finished episode (Monitor.step,
-// monitor_wrapper.py:131).
+// np.median of the first n entries of hist (non-negative floats) for Monitor.median_abs_torque_smoothed
+// (monitor_wrapper.py:102,131), computed by the G lanes of an environment: the values are staged in the environment's
+// (by then dead) shared-memory scratch and the middle order statistic is found by a radix select, 8 bits per pass with
+// a 256-bin histogram.  Called by every lane of the warp at the end of a step in which an episode ended; n may differ
+// between the two environments of a warp, n == 0 returns 0.  scratch: cap floats + 256 ints of this environment.
 template <int G>
-__device__ __noinline__ float group_median(const float* __restrict__ hist, int n, int l) {
+__device__ __noinline__ float group_median(const float* __restrict__ hist, float* scratch, int cap, int n, int l) {
+  unsigned* keys = reinterpret_cast<unsigned*>(scratch);
+  int* bins = reinterpret_cast<int*>(scratch + cap);
+  const int ns = n < cap ? n : cap;                     // staged part; a longer episode reads the rest from global
+  for (int i = l; i < ns; i += G) keys[i] = __float_as_uint(hist[i]);
+  __syncwarp();
+  auto key_at = [&](int i) -> unsigned { return i < ns ? keys[i] : __float_as_uint(hist[i]); };
   const int nmax = __reduce_max_sync(kFull, n);
-  float res[2] = {0.f, 0.f};
+  int k = (n - 1) / 2;                                  // lower middle
+  unsigned prefix = 0u;
 #pragma unroll 1
-  for (int which = 0; which < 2; which++) {
-    const int k = which == 0 ? (n - 1) / 2 : n / 2;       // lower / upper middle (equal for odd n)
-    unsigned prefix = 0u;
-#pragma unroll 1
-    for (int bit = 30; bit >= 0; bit--) {
-      const unsigned cand = prefix | (1u << bit);
-      int cnt = 0;
-      for (int i = l; i < nmax; i += G)
-        if (i < n && __float_as_uint(hist[i]) < cand) cnt++;
-      cnt = group_sum_int<G>(cnt);
-      if (cnt <= k) prefix = cand;
+  for (int shift = 24; shift >= 0; shift -= 8) {
+    for (int i = l; i < 256; i += G) bins[i] = 0;
+    __syncwarp();
+    for (int i = l; i < nmax; i += G) {
+      if (i < n) {
+        const unsigned key = key_at(i);
+        if (shift == 24 || (key >> (shift + 8)) == prefix) atomicAdd(&bins[(key >> shift) & 255u], 1);
+      }
     }
-    res[which] = __uint_as_float(prefix);
+    __syncwarp();
+    // bucket holding rank k: every lane sums 256 / G consecutive bins, a scan over the lanes finds the lane, which
+    // then walks its own bins
+    constexpr int kPer = 256 / G;
+    int mine = 0;
+#pragma unroll
+    for (int j = 0; j < kPer; j++) mine += bins[l * kPer + j];
+    int incl = mine;
+#pragma unroll
+    for (int o = 1; o < G; o <<= 1) {
+      const int t = __shfl_up_sync(kFull, incl, o, G);
+      if (l >= o) incl += t;
+    }
+    const int before = incl - mine;
+    const bool owner = n > 0 && k >= before && k < incl;
+    int bucket = 0, kk = 0;
+    if (owner) {
+      int acc = before;
+      for (int j = 0; j < kPer; j++) {
+        const int c = bins[l * kPer + j];
+        if (k < acc + c) { bucket = l * kPer + j; kk = k - acc; break; }
+        acc += c;
+      }
+    }
+    // broadcast from the owning lane of this environment (exactly one when n > 0)
+    const unsigned own_mask = __ballot_sync(kFull, owner);
+    const unsigned grp = (G == 32) ? kFull : (0xFFFFu << (16 * ((threadIdx.x & 31) / 16)));
+    const int src = (own_mask & grp) ? __ffs(own_mask & grp) - 1 : 0;
+    bucket = __shfl_sync(kFull, bucket, src);
+    kk = __shfl_sync(kFull, kk, src);
+    prefix = (prefix << 8) | (unsigned)bucket;
+    k = kk;
+    __syncwarp();
   }
-  return n > 0 ? 0.5f * (res[0] + res[1]) : 0.f;
+  const unsigned lo = prefix;
+  // upper middle (even n): the same value when it is repeated, else the smallest value above it
+  unsigned hi = lo;
+  if ((nmax > 0) && true) {
+    int cnt_le = 0;
+    unsigned min_gt = 0xFFFFFFFFu;
+    for (int i = l; i < nmax; i += G) {
+      if (i < n) {
+        const unsigned key = key_at(i);
+        if (key <= lo) cnt_le++;
+        else min_gt = key < min_gt ? key : min_gt;
+      }
+    }
+    cnt_le = group_sum_int<G>(cnt_le);
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) {
+      const unsigned t = __shfl_xor_sync(kFull, min_gt, o);
+      min_gt = t < min_gt ? t : min_gt;
+    }
+    if ((n & 1) == 0 && cnt_le < n / 2 + 1) hi = min_gt;
+  }
+  return n > 0 ? 0.5f * (__uint_as_float(lo) + __uint_as_float(hi)) : 0.f;
 }
 
 // desired walking velocity vector (straight:417-422,479-480 / loco3d:51-97)
@@ -510,7 +568,10 @@ __global__ void __launch_bounds__(128, 4) mimic_step_kernel(const StepArgs A, co
     __syncwarp();
     if (__any_sync(kFull, done)) {
       const int nh = ep_len_now < M.ep_dur_max ? ep_len_now : M.ep_dur_max;
-      med_tor = group_median<G>(hist, (done && live) ? nh : 0, l);
+      // scratch: this environment's solver arrays up to (not including) the statistics row in E.Mt
+      float* scratch = &E.S[0][0];
+      const int cap = (int)((reinterpret_cast<float*>(E.Mt) - scratch)) - 256;
+      med_tor = group_median<G>(hist, scratch, cap, (done && live) ? nh : 0, l);
     }
   }
   double* sd = A.state_d + (size_t)env * 4;

@@ -219,8 +219,9 @@ class B200MimicVecEnv:
         c.lanes_per_env = lanes_per_env
         c.early_termination = int(bool(cfg.early_termination))
         hist_bytes = 4 * self.num_envs * max(1, cfg.ep_dur_max)
-        self._median_torque = bool(getattr(cfg, "median_torque", True)) and hist_bytes <= (1 << 30) \
-            and os.environ.get("DRLOCO_B200_MEDIAN_TORQUE", "1") != "0"          # developer hook for A/B timing
+        self._median_torque = bool(getattr(cfg, "median_torque", False))
+        if self._median_torque and hist_bytes > (4 << 30):
+            raise lib.DrlError(f"median_torque: the torque history would need {hist_bytes >> 20} MiB")
         c.monitor_median_torque = int(self._median_torque)
         return c
 

@@ -285,7 +285,9 @@ class _FrozenPhysics:
 
 def test_env_logic_and_monitor_on_injected_states():
     n, steps = 32, 60
-    env = _env(W3D, n, ep_dur_max=25)                            # short episodes: time-outs occur naturally (hypers.py:58)
+    from drloco_b200.vec_env import B200MimicVecEnv
+    # short episodes: time-outs occur naturally (hypers.py:58); the torque history for Monitor's median statistic is on
+    env = B200MimicVecEnv(W3D, num_envs=n, cfg=EnvConfig(env_id=W3D, ep_dur_max=25, median_torque=True), seed=5)
     spec = env.spec
     env.debug_set(frame_skip_override=0)
     ora = _oracle(spec, n, physics=lambda: _FrozenPhysics(spec.model))

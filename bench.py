@@ -69,17 +69,20 @@ def _peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled during the timed region.  nvidia-smi takes up to a second to start on
+    an 8-GPU box while a timed region lasts tens of milliseconds, so the sampler is started well before (`start`), every
+    sample is stamped with the host clock, and only the samples between `begin()` and `end()` are reported."""
 
     def __init__(self, index: int):
         self.index, self.rows, self.proc = index, [], None
+        self.t0 = self.t1 = None
 
     def start(self):
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}",
-                                          "--format=csv,noheader,nounits", "-lms", "20"],
+                                          "--format=csv,noheader,nounits", "-lms", "10"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except OSError:
@@ -87,19 +90,28 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
+
+    def begin(self):
+        self.t0 = time.time()
+
+    def end(self):
+        self.t1 = time.time()
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.05)
         self.proc.terminate()
-        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
-        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        t0, t1 = self.t0 or 0.0, (self.t1 or time.time()) + 0.02       # a sample is printed up to one period late
+        inside = [r for t, r in self.rows if t0 <= t <= t1]
+        rows = inside if inside else [r for _, r in self.rows[-3:]]      # (region shorter than one period)
+        sm = sorted(int(r[0]) for r in rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in rows if len(r) > 1 and r[1].isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[k] for r in self.rows if len(r) >= 6 for k in range(4) if r[2 + k].lower() == "active"})
+        reasons = sorted({names[k] for r in rows if len(r) >= 6 for k in range(4) if r[2 + k].lower() == "active"})
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(sm)}
+                "samples": len(sm), "samples_inside_timed_regions": len(inside)}
 
 
 def fp32_peak_tflops(device_index: int) -> float:
@@ -296,7 +308,8 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        import datetime
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(seconds=180))
     dev = torch.device("cuda", local)
     flush = torch.empty(192 * 1024 * 1024 // 4, device=dev)                    # > 126 MB L2
 
@@ -313,6 +326,9 @@ def main():
 
     def measure(env_id, n, integrator, steps, warmup, with_clocks=False, flushed_steps=0, e2e_steps=0):
         """one workload on this rank's GPU: W warm-up steps, then K timed steps of every flavour"""
+        sampler = ClockSampler(local) if with_clocks else None
+        if sampler:
+            sampler.start()
         cfg = EnvConfig(env_id=env_id, integrator=integrator)
         env = B200MimicVecEnv(env_id, num_envs=n, device=f"cuda:{local}", seed=rank, cfg=cfg, env_id_offset=rank * n)
         vn = B200VecNormalize(env, distributed=world > 1)
@@ -327,9 +343,8 @@ def main():
         barrier()
         env.reset_stats()
         # ---- device-resident, statistics chain overlapped (value) + per-kernel timing of the fused step kernel ----
-        sampler = ClockSampler(local) if with_clocks else None
         if sampler:
-            sampler.start()
+            sampler.begin()
         launches0 = env.launches + vn.launches
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
         kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
@@ -348,8 +363,6 @@ def main():
         vn.synchronize()
         ev[1].record()
         barrier()
-        if sampler:
-            out["clocks"] = sampler.stop()
         ms_total = max_over_ranks(ev[0].elapsed_time(ev[1]))
         out["ms_per_step"] = ms_total / steps
         out["value"] = world * n * steps / (ms_total * 1e-3)
@@ -364,6 +377,9 @@ def main():
             vn.step_tensor(ring[k % 64])                 # wait=True: step -> exchange/merge/normalise, serialised
         ev[1].record()
         barrier()
+        if sampler:                                      # the clocks cover the value and value_serialized regions
+            sampler.end()
+            out["clocks"] = sampler.stop()
         ms_ser = max_over_ranks(ev[0].elapsed_time(ev[1]))
         out["value_serialized"] = world * n * steps / (ms_ser * 1e-3)
         # ---- every step timed alone after an L2 flush (cold persistent state) ----
@@ -421,7 +437,9 @@ def main():
                                            "per GPU x %d" % world, "value": m3["value"],
                                "value_serialized": m3["value_serialized"], "ms_per_step": m3["ms_per_step"],
                                "kernel_ms": m3["kernel_ms"], "steps": 20, "warmup": 5,
-                               "mean_ep_len": m3["stats"]["ep_len_sum"] / max(1.0, m3["stats"]["episodes"])}
+                               "episodes_finished": m3["stats"]["episodes"],
+                               "mean_ep_len": (m3["stats"]["ep_len_sum"] / m3["stats"]["episodes"]
+                                               if m3["stats"]["episodes"] else None)}
 
     if rank == 0:
         peaks, which = _peaks()

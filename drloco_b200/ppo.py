@@ -266,7 +266,8 @@ def evaluate_walking(policy: ActorCritic, train_env, n_episodes: int = 20, min_s
     spec = venv.spec
     t = spec.mocap
     env = B200MimicVecEnv(spec.cfg.env_id, num_envs=n_episodes, device=venv.device, cfg=spec.cfg, spec=spec, seed=0)
-    vn = B200VecNormalize(env, training=False, norm_reward=False)
+    # a local, single-process wrapper: the evaluation may run on one rank only (no collective at construction)
+    vn = B200VecNormalize(env, training=False, norm_reward=False, distributed=False)
     vn.load_state_dict({**train_env.state_dict(), "norm_reward": False})
     # the reference plays EVAL_N_TIMES consecutive episodes in one env in evaluation mode (callback.py:286-297); here
     # env i plays episode i: deterministic init i, including the reference's table aliasing

@@ -579,7 +579,9 @@ class B200VecNormalize:
             raise ValueError("reset_update must be 'sb3-1.0' or 'obs'")
         self.venv = venv
         self.num_envs, self.device = venv.num_envs, venv.device
-        self.observation_space, self.action_space = venv.observation_space, venv.action_space
+        # the wrapper hands out float32 observations (what SB3 converts them to anyway); its space says so
+        self.observation_space = Box(-np.inf, np.inf, (venv.obs_dim,), np.float32)
+        self.action_space = venv.action_space
         self.training, self.norm_obs, self.norm_reward = training, norm_obs, norm_reward
         self.clip_obs, self.clip_reward, self.gamma, self.epsilon = clip_obs, clip_reward, gamma, epsilon
         self.reset_update = reset_update

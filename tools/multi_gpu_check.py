@@ -42,7 +42,8 @@ def run(exchange, n, steps, rank, local, every=1):
 def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import datetime
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(seconds=90))
     n, steps = 1024, 25
     out = {"world": world}
     ok = True

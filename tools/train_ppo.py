@@ -40,7 +40,10 @@ def main():
     rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", "0"), ("WORLD_SIZE", "1"), ("LOCAL_RANK", "0")))
     if world > 1:
         torch.cuda.set_device(local)
-        torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local))
+        import datetime
+        # a short collective timeout: a rank that falls out of step must fail the run quickly, not hold the GPUs
+        torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local),
+                                             timeout=datetime.timedelta(seconds=90))
     if args.cpu_oracle:
         from tools.oracle_tensor_env import OracleTensorEnv
         env = OracleTensorEnv("StraightMimicWalker", args.envs, seed=33 + args.seed)

@@ -443,18 +443,20 @@ extern "C" int drl_vecnorm_terminal(const float* tobs_in, float* tobs_out, const
 
 // The same, compacted: only the rows of finished environments leave the device.  out = 4 header words (out[0] = number of
 // finished environments) followed by one record per finished environment, record = { env index (int32 bits), d floats }.
-// Record order is arbitrary (one atomic slot per finished row); the host maps rows back through the index.
+// Record order is arbitrary (one atomic slot per finished row); the host maps rows back through the index.  `out` may
+// be device memory or pinned host memory mapped into the device's address space (the records are then written across
+// PCIe by the kernel itself: no copy node).  counters: device int32 [2] = { slot counter, block ticket }, zero before the
+// first launch; the last block to finish publishes the count in the header and zeroes both again.
 namespace drl {
 __global__ void vecnorm_terminal_compact_kernel(const float* __restrict__ tin, const unsigned char* __restrict__ done,
                                                 int n, int d, const double* __restrict__ rms, float clip_obs, float eps,
-                                                int norm_obs, float* __restrict__ out) {
+                                                int norm_obs, float* __restrict__ out, int* __restrict__ counters) {
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarp = (gridDim.x * blockDim.x) >> 5;
-  int* hdr = reinterpret_cast<int*>(out);
   for (int row = warp; row < n; row += nwarp) {
     if (!done[row]) continue;
     int slot = 0;
-    if (lane == 0) slot = atomicAdd(hdr, 1);
+    if (lane == 0) slot = atomicAdd(&counters[0], 1);
     slot = __shfl_sync(0xFFFFFFFFu, slot, 0);
     float* rec = out + 4 + (size_t)slot * (d + 1);
     if (lane == 0) reinterpret_cast<int*>(rec)[0] = row;
@@ -465,19 +467,29 @@ __global__ void vecnorm_terminal_compact_kernel(const float* __restrict__ tin, c
       rec[1 + col] = x;
     }
   }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(&counters[1], 1) == (int)gridDim.x - 1) {
+      __threadfence();
+      reinterpret_cast<int*>(out)[0] = *reinterpret_cast<volatile int*>(&counters[0]);
+      counters[0] = 0;
+      counters[1] = 0;
+      __threadfence_system();
+    }
+  }
 }
 }  // namespace drl
 
 extern "C" int drl_vecnorm_terminal_compact(const float* tobs_in, const uint8_t* done, int32_t n, int32_t d,
                                             const double* rms, float clip_obs, float eps, int32_t norm_obs,
-                                            float* out_words, void* stream) {
-  if (!tobs_in || !done || !out_words || n <= 0 || d <= 0 || (norm_obs && !rms)) return DRL_ERR_INVALID;
+                                            float* out_words, int32_t* counters, void* stream) {
+  if (!tobs_in || !done || !out_words || !counters || n <= 0 || d <= 0 || (norm_obs && !rms)) return DRL_ERR_INVALID;
   cudaStream_t st = (cudaStream_t)stream;
-  if (cudaMemsetAsync(out_words, 0, 16, st) != cudaSuccess) return DRL_ERR_CUDA;
   int blocks = (n * 32 + drl::kVnThreads - 1) / drl::kVnThreads;
-  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks > 148 * 4) blocks = 148 * 4;
   drl::vecnorm_terminal_compact_kernel<<<blocks, drl::kVnThreads, 0, st>>>(tobs_in, done, n, d, rms, clip_obs, eps,
-                                                                         norm_obs, out_words);
+                                                                         norm_obs, out_words, counters);
   return cudaGetLastError() == cudaSuccess ? DRL_OK : DRL_ERR_CUDA;
 }
 

@@ -79,29 +79,32 @@ class LazyInfos(Sequence):
 
 
 class _TerminalRows:
-    """device -> host path of the terminal observations: the rows of finished environments are compacted on the device
-    (csrc/vecnorm.cu::vecnorm_terminal_compact_kernel) and a fixed-size prefix of the record buffer travels with the
-    step's other outputs; the rest is fetched only when more environments finished than the prefix holds."""
+    """device -> host path of the terminal observations: the rows of finished environments are compacted by
+    csrc/vecnorm.cu::vecnorm_terminal_compact_kernel into records { env index, d floats } behind a 4-word header.
+
+    Two modes.  own buffers (B200MimicVecEnv): records are compacted in device memory and a fixed-size prefix of the
+    record buffer is copied with the step's other outputs; the rest is fetched only when more environments finished
+    than the prefix holds.  host_words given (B200VecNormalize): the kernel writes the records straight into that
+    pinned host buffer (mapped into the device's address space) - no copy at all."""
 
     PREFIX = 256
 
-    def __init__(self, n: int, d: int, device, dev_words=None, host_words=None):
-        """dev_words / host_words: views of a larger output pack (B200VecNormalize) - the device view holds all records,
-        the pinned host view at least the prefix; None: own buffers, own prefix copy."""
+    def __init__(self, n: int, d: int, device, host_words=None):
         self.n, self.d, self.device = n, d, device
         self.words = self.words_for(n, d)
-        self.npre = self.prefix_words(n, d)
-        self.own_copy = dev_words is None
-        self.dev = torch.zeros(self.words, dtype=torch.float32, device=device) if dev_words is None else dev_words
-        self.set_host(torch.zeros(self.words, dtype=torch.float32).pin_memory() if host_words is None else host_words)
+        self.npre = 4 + min(n, self.PREFIX) * (d + 1)
+        self.counters = torch.zeros(2, dtype=torch.int32, device=device)
+        self.direct = host_words is not None
+        if self.direct:
+            self.dev = None
+            self.set_host(host_words)
+        else:
+            self.dev = torch.zeros(self.words, dtype=torch.float32, device=device)
+            self.set_host(torch.zeros(self.words, dtype=torch.float32).pin_memory())
 
     @staticmethod
     def words_for(n, d):
         return 4 + n * (d + 1)
-
-    @classmethod
-    def prefix_words(cls, n, d):
-        return 4 + min(n, cls.PREFIX) * (d + 1)
 
     def set_host(self, host_words):
         self.host = host_words
@@ -109,27 +112,24 @@ class _TerminalRows:
         self.host_i = self.host_np.view(np.int32)
 
     def enqueue(self, libh, tobs, done, rms, clip_obs, eps, norm_obs, stream_ptr):
+        dst = self.host if self.direct else self.dev
         lib.check(libh.drl_vecnorm_terminal_compact(_ptr(tobs), _ptr(done), self.n, self.d, _ptr(rms), float(clip_obs),
-                                                    float(eps), int(norm_obs), _ptr(self.dev), stream_ptr),
-                  "drl_vecnorm_terminal_compact")
-        if self.own_copy:
+                                                    float(eps), int(norm_obs), _ptr(dst), _ptr(self.counters),
+                                                    stream_ptr), "drl_vecnorm_terminal_compact")
+        if not self.direct:
             self.host[:self.npre].copy_(self.dev[:self.npre], non_blocking=True)
 
     def collect(self, dtype) -> dict:
-        """after the stream has been synchronised: {env index: terminal observation}"""
+        """after the stream has been synchronised: {env index: {"terminal_observation": row}}"""
         cnt = int(self.host_i[0])
         if cnt == 0:
             return {}
         need = 4 + cnt * (self.d + 1)
-        src_np, src_i = self.host_np, self.host_i
-        if need > self.npre:                             # more finished environments than the prefix holds (rare)
-            full = torch.zeros(need, dtype=torch.float32).pin_memory()
-            full.copy_(self.dev[:need], non_blocking=True)
+        if not self.direct and need > self.npre:         # more finished environments than the prefix holds (rare)
+            self.host[self.npre:need].copy_(self.dev[self.npre:need], non_blocking=True)
             torch.cuda.current_stream(self.device).synchronize()
-            src_np = full.numpy()
-            src_i = src_np.view(np.int32)
-        rec = src_np[4:need].reshape(cnt, self.d + 1)
-        idx = src_i[4:need].reshape(cnt, self.d + 1)[:, 0]
+        rec = self.host_np[4:need].reshape(cnt, self.d + 1)
+        idx = self.host_i[4:need].reshape(cnt, self.d + 1)[:, 0]
         rows = rec[:, 1:].astype(dtype)                  # one copy = fresh memory for all terminal observations
         return {int(i): {"terminal_observation": rows[k]} for k, i in enumerate(idx.tolist())}
 
@@ -689,14 +689,17 @@ class B200VecNormalize:
         lib.check(self._lib.drl_attach_vecnorm(self.venv._handle, _ptr(self.ret), float(self.gamma),
                                                _ptr(self._packed[self._k ^ 1])), "drl_attach_vecnorm")
 
-    def _normalize(self, obs, rew, done, wait=True, packed=None, upd_obs=None, upd_ret=None, immediate=False):
+    def _normalize(self, obs, rew, done, wait=True, packed=None, upd_obs=None, upd_ret=None, immediate=False,
+                   out=None):
         """enqueue the exchange + merge + normalisation kernel for the env outputs just produced on the current stream.
         wait=True makes the current stream wait for the result (normal use); wait=False leaves it running on the side
         stream (``synchronize()`` / the next ``wait=True`` call / a stream sync picks it up)."""
         main = torch.cuda.current_stream(self.device)
         self._k ^= 1
         k = self._k
-        nobs, nrew = self._nobs[k], self._nrew[k]
+        # out: (obs, rew, done) destinations other than this buffer set's device pack - the numpy API passes pinned host
+        # tensors, which the kernel then fills across PCIe itself
+        nobs, nrew, ndone = out if out is not None else (self._nobs[k], self._nrew[k], self._ndone[k])
         if packed is None:
             packed = self._packed[k]
         upd_obs = self.training if upd_obs is None else upd_obs
@@ -738,7 +741,7 @@ class B200VecNormalize:
             src, dst = self._rms[self._cur], self._rms[1 - self._cur]
             lib.check(self._lib.drl_vecnorm_step(_ptr(obs), _ptr(nobs), _ptr(rew), _ptr(nrew) if rew is not None else None,
                                                  self.num_envs, self._D, _ptr(packed), _ptr(src), _ptr(dst),
-                                                 _ptr(self.ret), _ptr(done), _ptr(self._ndone[k]),
+                                                 _ptr(self.ret), _ptr(done), _ptr(ndone),
                                                  float(self.clip_obs), float(self.clip_reward), float(self.epsilon),
                                                  flags, self._comm,
                                                  int(sync_every), C.c_void_p(stream.cuda_stream)), "drl_vecnorm_step")
@@ -805,25 +808,25 @@ class B200VecNormalize:
     def _host_buffers(self):
         if not hasattr(self, "_h"):
             N, D, A = self.num_envs, self._D, self.venv.act_dim
-            n_copy = self._w_head + _TerminalRows.prefix_words(N, D)
-            self._n_copy = n_copy
-            hp = [torch.zeros(n_copy).pin_memory() for _ in range(2)]            # two alternating host packs
-            self._h = dict(act=torch.zeros(N, A).pin_memory(), pack=hp)
-            self._h_np = dict(act=self._h["act"].numpy(),
-                              obs=[p[:self._w_obs].view(N, D).numpy() for p in hp],
-                              rew=[p[self._w_obs:self._w_obs + N].numpy() for p in hp],
-                              done=[p[self._w_obs + N:self._w_head].view(torch.uint8)[:N].numpy() for p in hp])
+            # two alternating pinned host packs with the layout of the device packs; the kernels write into them directly
+            # (pinned host memory is mapped into the device's address space), so a numpy-API step has no D2H copy node
+            hp = [torch.zeros(self._w_head + _TerminalRows.words_for(N, D)).pin_memory() for _ in range(2)]
+            self._h = dict(act=torch.zeros(N, A).pin_memory(), pack=hp,
+                           obs=[p[:self._w_obs].view(N, D) for p in hp],
+                           rew=[p[self._w_obs:self._w_obs + N] for p in hp],
+                           done=[p[self._w_obs + N:self._w_head].view(torch.uint8)[:N] for p in hp])
+            self._h_np = dict(act=self._h["act"].numpy(), obs=[t.numpy() for t in self._h["obs"]],
+                              rew=[t.numpy() for t in self._h["rew"]], done=[t.numpy() for t in self._h["done"]])
             self._hk = 0
             self._d_act = torch.zeros(N, A, device=self.device)
-            self._trows = [_TerminalRows(N, D, self.device, dev_words=self._pack[k][self._w_head:],
-                                         host_words=hp[0][self._w_head:]) for k in range(2)]
+            self._trows = [_TerminalRows(N, D, self.device, host_words=p[self._w_head:]) for p in hp]
         return self._h
 
     def reset(self, inject=None):
         h = self._host_buffers()
         self._hk ^= 1
         nobs = self.reset_tensor(inject)
-        h["pack"][self._hk][:self._w_obs].copy_(nobs.reshape(-1), non_blocking=True)
+        h["obs"][self._hk].copy_(nobs, non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()
         o = self._h_np["obs"][self._hk]
         return o.copy() if self.copy_outputs else o
@@ -836,18 +839,20 @@ class B200VecNormalize:
     def _enqueue_step(self, inject=None):
         h = self._h
         self._d_act.copy_(h["act"], non_blocking=True)
-        obs, rew, done = self.step_tensor(self._d_act, inject)
-        k = self._k
+        self._guard_reuse()
+        self._attach_next()
+        obs, rew, done = self.venv.step_tensor(self._d_act, inject)
         self._hk ^= 1
+        hk = self._hk
+        # exchange + merge + normalise, results written straight into the pinned host pack
+        self._normalize(obs, rew, done, True, out=(h["obs"][hk], h["rew"][hk], h["done"][hk]))
         with torch.cuda.device(self.device):
             # terminal observations normalised with the statistics just merged (SB3 VecNormalize.step_wait), compacted
-            # into the tail of this step's output pack
-            self._trows[k].enqueue(self._lib, self.venv.terminal_obs, done, self._rms[self._cur], self.clip_obs,
-                                   self.epsilon, self.norm_obs, self.venv._stream())
+            # into the tail of the same host pack
+            self._trows[hk].enqueue(self._lib, self.venv.terminal_obs, done, self._rms[self._cur], self.clip_obs,
+                                    self.epsilon, self.norm_obs, self.venv._stream())
         self.launches += 1
-        # obs | rew | done | terminal-record prefix: one copy
-        h["pack"][self._hk].copy_(self._pack[k][:self._n_copy], non_blocking=True)
-        self._last = (k, self._hk)
+        self._last = hk
 
     def _graph_key(self):
         v = self.venv
@@ -889,7 +894,7 @@ class B200VecNormalize:
         g, after, dl = entry
         g.replay()
         v._cur, self._k, self._cur, self._hk = after
-        self._last = (self._k, self._hk)
+        self._last = self._hk
         self._calls += 1
         v.launches += dl[0]
         self.launches += dl[1]
@@ -904,13 +909,11 @@ class B200VecNormalize:
     def step_wait(self):
         hn = self._h_np
         torch.cuda.current_stream(self.device).synchronize()
-        k, hk = self._last
+        hk = self._last
         done = hn["done"][hk].astype(bool)
-        tr = self._trows[k]
-        tr.set_host(self._h["pack"][hk][self._w_head:])
-        infos = LazyInfos(self.num_envs, tr.collect(np.float32))
+        infos = LazyInfos(self.num_envs, self._trows[hk].collect(np.float32))
         if self.copy_outputs:
-            obs = self._h["pack"][hk][:self._w_obs].view(self.num_envs, self._D).clone().numpy()   # multi-threaded copy
+            obs = self._h["obs"][hk].clone().numpy()                 # multi-threaded copy out of the pinned buffer
         else:
             obs = hn["obs"][hk]
         return obs, hn["rew"][hk].copy(), done, infos
@@ -923,9 +926,9 @@ class B200VecNormalize:
         return self.num_envs * self.venv.act_dim * 4
 
     def d2h_bytes_per_step(self) -> int:
-        """obs + reward + done + the terminal-record prefix (more only when > _TerminalRows.PREFIX envs finish)"""
-        self._host_buffers()
-        return self._n_copy * 4
+        """bytes the kernels write into the pinned host pack per step: obs + reward + done + record header (+ one record of
+        (D + 1) words per finished environment, not counted here)"""
+        return self._w_head * 4 + 16
 
     def normalize_obs(self, obs: torch.Tensor) -> torch.Tensor:
         if not self.norm_obs:

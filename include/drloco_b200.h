@@ -300,11 +300,15 @@ int drl_vecnorm_step(const float* obs_in, float* obs_out, const float* rew_in, f
 int drl_vecnorm_terminal(const float* tobs_in, float* tobs_out, const uint8_t* done, int32_t n, int32_t d,
                          const double* rms, float clip_obs, float eps, int32_t norm_obs, void* stream);
 
-/* the same, compacted on the device so that only finished environments cross PCIe: out_words (device, 4 + n*(d+1) 32-bit
- * words) = header { count, 0, 0, 0 } + one record { env index (int32), d floats } per finished environment, in
- * arbitrary order.  rms may be NULL when norm_obs == 0 (raw terminal observations). */
+/* the same, compacted so that only finished environments cross PCIe: out_words (4 + n*(d+1) 32-bit words) = header
+ * { count, -, -, - } + one record { env index (int32), d floats } per finished environment, in arbitrary order.
+ * out_words may be device memory or pinned host memory (mapped into the device's address space: the kernel then writes
+ * the records across PCIe itself).  The same holds for obs_out / rew_out / done_out of drl_vecnorm_step.
+ * counters: device int32 [2], zero before the first call, left zero by every call (slot counter, block ticket).
+ * rms may be NULL when norm_obs == 0 (raw terminal observations). */
 int drl_vecnorm_terminal_compact(const float* tobs_in, const uint8_t* done, int32_t n, int32_t d, const double* rms,
-                                 float clip_obs, float eps, int32_t norm_obs, float* out_words, void* stream);
+                                 float clip_obs, float eps, int32_t norm_obs, float* out_words, int32_t* counters,
+                                 void* stream);
 
 /* measured sustained FFMA rate of `device` in TFLOP/s (8 independent FMA chains per thread, all SMs): the FP32
  * roofline denominator bench.py reports next to the HBM one. Synchronises the device. */

@@ -280,6 +280,9 @@ def main():
                     help="informational runs of the other BASELINE.json configs; the headline is the default")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--stats-sync-every", type=int, default=1,
+                    help="B200VecNormalize(stats_sync_every=K): exchange / merge the VecNormalize moments every K-th step "
+                         "(opt-in amortisation; 1 = SB3 semantics, the headline setting)")
     ap.add_argument("--no-extra", action="store_true", help="skip the time-bounded legs for BASELINE.json configs[2] / [3]")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -331,7 +334,7 @@ def main():
             sampler.start()
         cfg = EnvConfig(env_id=env_id, integrator=integrator)
         env = B200MimicVecEnv(env_id, num_envs=n, device=f"cuda:{local}", seed=rank, cfg=cfg, env_id_offset=rank * n)
-        vn = B200VecNormalize(env, distributed=world > 1)
+        vn = B200VecNormalize(env, distributed=world > 1, stats_sync_every=args.stats_sync_every)
         g = torch.Generator(device=dev)
         g.manual_seed(1234 + rank)
         ring = torch.rand(64, n, env.act_dim, device=dev, generator=g) * 2 - 1     # pre-generated action ring (§8d)
@@ -461,6 +464,7 @@ def main():
                                     "termination (BASELINE.json configs[3])" % n),
                        "envs_per_gpu": n, "integrator": args.integrator, "frame_skip": head["frame_skip"],
                        "parallelism": f"env-sharded x{world}", "statistics_exchange": head["exchange"],
+                       "stats_sync_every": args.stats_sync_every,
                        "l2": "value / value_serialized: the persistent env state (%.1f MB) is re-read every step as in "
                              "a real rollout; value_l2_flushed: every step re-timed alone after a 192 MB L2 flush"
                              % (n * 720 / 1e6),

@@ -283,6 +283,8 @@ def main():
     ap.add_argument("--stats-sync-every", type=int, default=1,
                     help="B200VecNormalize(stats_sync_every=K): exchange / merge the VecNormalize moments every K-th step "
                          "(opt-in amortisation; 1 = SB3 semantics, the headline setting)")
+    ap.add_argument("--host-outputs", choices=["mapped", "copy"], default="mapped",
+                    help="numpy API: kernels write the outputs into mapped pinned host memory, or one D2H copy per step")
     ap.add_argument("--no-extra", action="store_true", help="skip the time-bounded legs for BASELINE.json configs[2] / [3]")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -402,7 +404,8 @@ def main():
         if e2e_steps:
             host_actions = [np.random.default_rng(rank * 1000 + k).uniform(-1, 1, (n, env.act_dim)).astype(np.float32)
                             for k in range(8)]
-            for k in range(3):
+            vn.host_outputs = args.host_outputs
+            for k in range(5):
                 vn.step(host_actions[k % 8])
             barrier()
             flush.fill_(1.0)
@@ -419,14 +422,14 @@ def main():
             t2 = max_over_ranks(ev2[0].elapsed_time(ev2[1]))
             out["e2e"] = {"value": world * n * e2e_steps / (t2 * 1e-3), "unit": "env-steps/s",
                           "h2d_bytes_per_step": vn.h2d_bytes_per_step(), "d2h_bytes_per_step": vn.d2h_bytes_per_step(),
-                          "steps": e2e_steps,
+                          "steps": e2e_steps, "host_outputs": vn.host_outputs,
                           "api": "B200VecNormalize.step(host float32 actions) -> host obs, rew, done, infos (defaults)"}
         vn.close()
         return out
 
     n = args.envs_per_gpu
     head = measure(args.env_id, n, args.integrator, args.steps, args.warmup, with_clocks=True,
-                   flushed_steps=min(args.steps, 50), e2e_steps=0 if args.no_e2e else max(10, args.steps // 4))
+                   flushed_steps=min(args.steps, 50), e2e_steps=0 if args.no_e2e else args.steps)
     # ---- the other GPU configurations of BASELINE.json, time-bounded (a few dozen steps each) ----
     extra = {}
     if not args.no_extra and args.env_id == ENV_ID and args.integrator == "rk4":

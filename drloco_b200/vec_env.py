@@ -82,21 +82,26 @@ class _TerminalRows:
     """device -> host path of the terminal observations: the rows of finished environments are compacted by
     csrc/vecnorm.cu::vecnorm_terminal_compact_kernel into records { env index, d floats } behind a 4-word header.
 
-    Two modes.  own buffers (B200MimicVecEnv): records are compacted in device memory and a fixed-size prefix of the
-    record buffer is copied with the step's other outputs; the rest is fetched only when more environments finished
-    than the prefix holds.  host_words given (B200VecNormalize): the kernel writes the records straight into that
-    pinned host buffer (mapped into the device's address space) - no copy at all."""
+    Three modes.  own buffers (B200MimicVecEnv): records are compacted in device memory and a fixed-size prefix of the
+    record buffer is copied to pinned host memory; the rest is fetched only when more environments finished than the
+    prefix holds.  host_words only (B200VecNormalize, host_outputs="mapped"): the kernel writes the records straight
+    into that pinned host buffer (mapped into the device's address space) - no copy at all.  dev_words + host_words
+    (host_outputs="copy"): both are tails of a larger output pack whose head-plus-prefix the caller copies itself."""
 
     PREFIX = 256
 
-    def __init__(self, n: int, d: int, device, host_words=None):
+    def __init__(self, n: int, d: int, device, host_words=None, dev_words=None):
         self.n, self.d, self.device = n, d, device
         self.words = self.words_for(n, d)
         self.npre = 4 + min(n, self.PREFIX) * (d + 1)
         self.counters = torch.zeros(2, dtype=torch.int32, device=device)
-        self.direct = host_words is not None
+        self.direct = host_words is not None and dev_words is None
+        self.own_copy = host_words is None
         if self.direct:
             self.dev = None
+            self.set_host(host_words)
+        elif dev_words is not None:
+            self.dev = dev_words
             self.set_host(host_words)
         else:
             self.dev = torch.zeros(self.words, dtype=torch.float32, device=device)
@@ -116,7 +121,7 @@ class _TerminalRows:
         lib.check(libh.drl_vecnorm_terminal_compact(_ptr(tobs), _ptr(done), self.n, self.d, _ptr(rms), float(clip_obs),
                                                     float(eps), int(norm_obs), _ptr(dst), _ptr(self.counters),
                                                     stream_ptr), "drl_vecnorm_terminal_compact")
-        if not self.direct:
+        if self.own_copy:
             self.host[:self.npre].copy_(self.dev[:self.npre], non_blocking=True)
 
     def collect(self, dtype) -> dict:
@@ -804,12 +809,16 @@ class B200VecNormalize:
     # following `step`; SB3's collect_rollouts reads `_last_obs` during the next step and stores it right after, which
     # that covers) and saves one 0.5 MB host copy per step.
     copy_outputs = True
+    # "mapped": the kernels write the step's outputs straight into the pinned host pack (it is mapped into the device's
+    # address space) - no D2H copy node.  "copy": they write the device pack and one copy moves obs | reward | done |
+    # terminal-record prefix.  Set before the first numpy-API call.
+    host_outputs = "mapped"
 
     def _host_buffers(self):
         if not hasattr(self, "_h"):
+            assert self.host_outputs in ("mapped", "copy")
             N, D, A = self.num_envs, self._D, self.venv.act_dim
-            # two alternating pinned host packs with the layout of the device packs; the kernels write into them directly
-            # (pinned host memory is mapped into the device's address space), so a numpy-API step has no D2H copy node
+            # two alternating pinned host packs with the layout of the device packs
             hp = [torch.zeros(self._w_head + _TerminalRows.words_for(N, D)).pin_memory() for _ in range(2)]
             self._h = dict(act=torch.zeros(N, A).pin_memory(), pack=hp,
                            obs=[p[:self._w_obs].view(N, D) for p in hp],
@@ -819,7 +828,13 @@ class B200VecNormalize:
                               rew=[t.numpy() for t in self._h["rew"]], done=[t.numpy() for t in self._h["done"]])
             self._hk = 0
             self._d_act = torch.zeros(N, A, device=self.device)
-            self._trows = [_TerminalRows(N, D, self.device, host_words=p[self._w_head:]) for p in hp]
+            if self.host_outputs == "mapped":
+                self._trows = [_TerminalRows(N, D, self.device, host_words=p[self._w_head:]) for p in hp]
+            else:
+                # indexed by the DEVICE pack's parity; the host view is set when the step is collected
+                self._trows = [_TerminalRows(N, D, self.device, host_words=hp[0][self._w_head:],
+                                             dev_words=self._pack[k][self._w_head:]) for k in range(2)]
+                self._n_copy = self._w_head + self._trows[0].npre
         return self._h
 
     def reset(self, inject=None):
@@ -844,15 +859,21 @@ class B200VecNormalize:
         obs, rew, done = self.venv.step_tensor(self._d_act, inject)
         self._hk ^= 1
         hk = self._hk
-        # exchange + merge + normalise, results written straight into the pinned host pack
-        self._normalize(obs, rew, done, True, out=(h["obs"][hk], h["rew"][hk], h["done"][hk]))
+        mapped = self.host_outputs == "mapped"
+        # exchange + merge + normalise; "mapped": results written straight into the pinned host pack
+        self._normalize(obs, rew, done, True, out=(h["obs"][hk], h["rew"][hk], h["done"][hk]) if mapped else None)
+        k = self._k
+        tr = self._trows[hk if mapped else k]
         with torch.cuda.device(self.device):
             # terminal observations normalised with the statistics just merged (SB3 VecNormalize.step_wait), compacted
-            # into the tail of the same host pack
-            self._trows[hk].enqueue(self._lib, self.venv.terminal_obs, done, self._rms[self._cur], self.clip_obs,
-                                    self.epsilon, self.norm_obs, self.venv._stream())
+            # into the tail of the same pack
+            tr.enqueue(self._lib, self.venv.terminal_obs, done, self._rms[self._cur], self.clip_obs, self.epsilon,
+                       self.norm_obs, self.venv._stream())
         self.launches += 1
-        self._last = hk
+        if not mapped:
+            # obs | rew | done | terminal-record prefix: one copy
+            h["pack"][hk][:self._n_copy].copy_(self._pack[k][:self._n_copy], non_blocking=True)
+        self._last = (tr, hk)
 
     def _graph_key(self):
         v = self.venv
@@ -894,7 +915,7 @@ class B200VecNormalize:
         g, after, dl = entry
         g.replay()
         v._cur, self._k, self._cur, self._hk = after
-        self._last = self._hk
+        self._last = (self._trows[self._hk if self.host_outputs == "mapped" else self._k], self._hk)
         self._calls += 1
         v.launches += dl[0]
         self.launches += dl[1]
@@ -909,9 +930,11 @@ class B200VecNormalize:
     def step_wait(self):
         hn = self._h_np
         torch.cuda.current_stream(self.device).synchronize()
-        hk = self._last
+        tr, hk = self._last
         done = hn["done"][hk].astype(bool)
-        infos = LazyInfos(self.num_envs, self._trows[hk].collect(np.float32))
+        if not tr.direct:
+            tr.set_host(self._h["pack"][hk][self._w_head:])
+        infos = LazyInfos(self.num_envs, tr.collect(np.float32))
         if self.copy_outputs:
             obs = self._h["obs"][hk].clone().numpy()                 # multi-threaded copy out of the pinned buffer
         else:
@@ -926,8 +949,11 @@ class B200VecNormalize:
         return self.num_envs * self.venv.act_dim * 4
 
     def d2h_bytes_per_step(self) -> int:
-        """bytes the kernels write into the pinned host pack per step: obs + reward + done + record header (+ one record of
-        (D + 1) words per finished environment, not counted here)"""
+        """"mapped": bytes the kernels write into the pinned host pack per step: obs + reward + done + record header (+ one
+        record of (D + 1) words per finished environment, not counted here); "copy": the size of the one copy"""
+        if self.host_outputs == "copy":
+            self._host_buffers()
+            return self._n_copy * 4
         return self._w_head * 4 + 16
 
     def normalize_obs(self, obs: torch.Tensor) -> torch.Tensor:

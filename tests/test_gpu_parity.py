@@ -581,12 +581,14 @@ def test_playback_ref_trajectories(env_id):
 # --------------------------------------------------------------------------------------------------------------------
 # VecNormalize kernels
 # --------------------------------------------------------------------------------------------------------------------
-def test_vecnormalize_matches_sb3_semantics():
+@pytest.mark.parametrize("host_outputs", ["mapped", "copy"])
+def test_vecnormalize_matches_sb3_semantics(host_outputs):
     from drloco_b200.vec_env import B200VecNormalize
     from oracle.env_oracle import RunningMeanStd
-    n = 256
+    n = 256 if host_outputs == "mapped" else 320          # 320 > _TerminalRows.PREFIX: the copy path's second fetch
     env = _env(W3D, n)
     vn = B200VecNormalize(env)
+    vn.host_outputs = host_outputs
     D = env.obs_dim
     obs_rms, ret_rms, ret = RunningMeanStd(shape=(D,)), RunningMeanStd(shape=()), np.zeros(n)
     rng = np.random.default_rng(4)
@@ -613,11 +615,14 @@ def test_vecnormalize_matches_sb3_semantics():
     q, v, c = env.get_state()
     q[:5, 2] = 0.45
     env.set_state(q, v, c)
+    if host_outputs == "copy":
+        q[:, 2] = 0.45                           # more finished envs than the copied record prefix holds
+        env.set_state(q, v, c)
     o, r, d, infos = vn.step(np.zeros((n, 8), np.float32))
-    assert d[:5].all()
+    assert d[:5].all() and (host_outputs == "mapped" or d.all())
     raw_t = env.terminal_obs.cpu().numpy().astype(np.float64)
     m, var = vn.obs_rms.mean, vn.obs_rms.var
-    for i in range(5):
+    for i in (range(5) if host_outputs == "mapped" else range(n)):
         want_t = np.clip((raw_t[i] - m) / np.sqrt(var + 1e-8), -10, 10)
         assert np.abs(infos[i]["terminal_observation"] - want_t).max() < 2e-4
     assert all("terminal_observation" not in infos[i] for i in np.nonzero(~d)[0])

@@ -343,6 +343,12 @@ def main():
         out = {"exchange": vn.exchange, "frame_skip": env.spec.frame_skip, "act_dim": env.act_dim,
                "obs_dim": env.obs_dim, "lanes_per_env": env.launch_info()["lanes_per_env"]}
         vn.reset_tensor()
+        if with_clocks:
+            # headline leg on a box that may just have been idle: ~0.4 s of untimed steps so that clocks / power state
+            # are up before the W warm-up steps (a cold box ran the first 200 steps 5 % slower; fixed count, every rank
+            # takes part in each step's exchange)
+            for k in range(1500):
+                vn.step_tensor(ring[k % 64])
         for k in range(warmup):
             vn.step_tensor(ring[k % 64])
         barrier()
@@ -468,6 +474,7 @@ def main():
                        "envs_per_gpu": n, "integrator": args.integrator, "frame_skip": head["frame_skip"],
                        "parallelism": f"env-sharded x{world}", "statistics_exchange": head["exchange"],
                        "stats_sync_every": args.stats_sync_every,
+                       "pre_warmup": "1500 untimed steps before the W warm-up steps (clock / power-state ramp)",
                        "l2": "value / value_serialized: the persistent env state (%.1f MB) is re-read every step as in "
                              "a real rollout; value_l2_flushed: every step re-timed alone after a 192 MB L2 flush"
                              % (n * 720 / 1e6),

@@ -411,7 +411,7 @@ def main():
             host_actions = [np.random.default_rng(rank * 1000 + k).uniform(-1, 1, (n, env.act_dim)).astype(np.float32)
                             for k in range(8)]
             vn.host_outputs = args.host_outputs
-            for k in range(5):
+            for k in range(10):                          # 2 eager steps, then one graph capture per buffer parity
                 vn.step(host_actions[k % 8])
             barrier()
             flush.fill_(1.0)

@@ -164,9 +164,12 @@ static int alloc_state(DrlEnv* e, size_t N) {
     // the smallest CTA the library launches carries 32 / G environments
     const size_t max_blocks = (N + (32 / e->G) - 1) / (32 / e->G);
     const size_t row = 2 * (size_t)e->cfg.obs_dim + 2 + DRL_STATS_COUNT;
-    CUDA_TRY(cudaMalloc(&e->cta_rows, max_blocks * row * sizeof(double)));
-    CUDA_TRY(cudaMalloc(&e->cta_ticket, sizeof(unsigned)));
-    CUDA_TRY(cudaMemset(e->cta_ticket, 0, sizeof(unsigned)));
+    // rows of the blocks, then one row per group of kStatGroup blocks (two-level fixed-order sum in the step kernel);
+    // tickets: [0] counts finished groups, [1 + g] the finished blocks of group g
+    const size_t max_groups = (max_blocks + kStatGroup - 1) / kStatGroup;
+    CUDA_TRY(cudaMalloc(&e->cta_rows, (max_blocks + max_groups) * row * sizeof(double)));
+    CUDA_TRY(cudaMalloc(&e->cta_ticket, (1 + max_groups) * sizeof(unsigned)));
+    CUDA_TRY(cudaMemset(e->cta_ticket, 0, (1 + max_groups) * sizeof(unsigned)));
   }
   CUDA_TRY(cudaMemset(e->state_f, 0, N * 4 * e->G * sizeof(float)));
   CUDA_TRY(cudaMemset(e->state_i, 0, N * kCurCount8 * sizeof(int)));

@@ -71,6 +71,7 @@ constexpr int kMiscCount = 16;
 constexpr int kCurIstep = 0, kCurPos = 1, kCurCount = 2, kCurEpDur = 3, kCurRsiStep = 4, kCurNDet = 5,
               kCurResets = 6, kCurFlags = 7;
 constexpr int kCurCount8 = 8;
+constexpr int kStatGroup = 16;        // blocks per group in the step kernel's two-level statistics sum
 
 struct StepArgs {
   const DevModel* model;
@@ -116,9 +117,10 @@ struct StepArgs {
   // Monitor.median_abs_torque_smoothed (monitor_wrapper.py:131): per-episode history of the mean |torque| of every step
   float* tor_hist;                   // [N][ep_dur_max], nullable (DrlConfig.monitor_median_torque)
   float* med_tor_sm;                 // [N] smoothed median, written at episode ends
-  // per-step statistics without atomics: every thread block writes one row of sums, the last block to finish adds them
-  double* cta_rows;                  // [grid][2*obs_dim + 2 + DRL_STATS_COUNT]
-  unsigned* cta_ticket;
+  // per-step statistics without atomics: every thread block writes one row of sums, the last block of every group of
+  // kStatGroup blocks adds the group's rows, the last group to finish adds the group rows
+  double* cta_rows;                  // [grid + groups][2*obs_dim + 2 + DRL_STATS_COUNT]
+  unsigned* cta_ticket;              // [1 + groups]
   // fused VecNormalize (drl_attach_vecnorm; null = not attached)
   float* vn_ret;                     // [N] discounted-return accumulator, in/out
   float vn_gamma;

@@ -697,40 +697,56 @@ __global__ void __launch_bounds__(128, 4) mimic_step_kernel(const StepArgs A, co
   }
   __threadfence();
   __syncthreads();
+  // two-level sum in a fixed order, whichever blocks end up doing it: the last block of a group of kStatGroup blocks
+  // adds the group's rows (one round of independent loads), the last group to finish adds the group rows and
+  // publishes: batch moments -> A.packed, statistics -> added to A.stats.  The serial tail behind the slowest block is
+  // two short rounds instead of one pass over every block's row.
   __shared__ unsigned s_ticket;
+  const unsigned grp = blockIdx.x / kStatGroup, ngroups = (gridDim.x + kStatGroup - 1) / kStatGroup;
+  const int gcount = min((int)kStatGroup, (int)gridDim.x - (int)grp * kStatGroup);
+  if (threadIdx.x == 0) s_ticket = atomicAdd(A.cta_ticket + 1 + grp, 1u);
+  __syncthreads();
+  if (s_ticket != (unsigned)gcount - 1u) return;
+  __threadfence();
+  double* grows = A.cta_rows + (size_t)gridDim.x * kRowLen;
+  for (int col = threadIdx.x; col < kRowLen; col += blockDim.x) {
+    const double* src = A.cta_rows + (size_t)grp * kStatGroup * kRowLen + col;
+    double p[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+    for (int r = 0; r < kStatGroup; r++)
+      if (r < gcount) p[r & 3] += __ldcg(src + (size_t)r * kRowLen);
+    grows[(size_t)grp * kRowLen + col] = (p[0] + p[1]) + (p[2] + p[3]);
+  }
+  if (threadIdx.x == 0) A.cta_ticket[1 + grp] = 0u;
+  __threadfence();
+  __syncthreads();
   if (threadIdx.x == 0) s_ticket = atomicAdd(A.cta_ticket, 1u);
   __syncthreads();
-  if (s_ticket == gridDim.x - 1) {
-    // the last block to finish adds up the blocks' rows, again in a fixed order (four interleaved partial sums per
-    // column keep the loads in flight), and publishes: batch moments -> A.packed, statistics -> added to A.stats
-    __threadfence();
-    const int nrows = (int)gridDim.x;
-    for (int col = threadIdx.x; col < kRowLen; col += blockDim.x) {
-      double p0 = 0.0, p1 = 0.0, p2 = 0.0, p3 = 0.0;
-      const double* src = A.cta_rows + col;
-      int r = 0;
-      for (; r + 3 < nrows; r += 4) {
-        p0 += __ldcg(src + (size_t)r * kRowLen);
-        p1 += __ldcg(src + (size_t)(r + 1) * kRowLen);
-        p2 += __ldcg(src + (size_t)(r + 2) * kRowLen);
-        p3 += __ldcg(src + (size_t)(r + 3) * kRowLen);
-      }
-      for (; r < nrows; r++) p0 += __ldcg(src + (size_t)r * kRowLen);
-      const double tot = (p0 + p1) + (p2 + p3);
-      if (col < kRowStats) {
-        if (A.packed) {
-          // packed layout of the VecNormalize kernels: [ sum obs[D], sumsq obs[D], n, sum ret, sumsq ret ]
-          const int D = M.obs_dim;
-          A.packed[col < 2 * D ? col : col + 1] = tot;
-        }
-      } else {
-        A.stats[col - kRowStats] += tot;
-      }
+  if (s_ticket != ngroups - 1u) return;
+  __threadfence();
+  for (int col = threadIdx.x; col < kRowLen; col += blockDim.x) {
+    double p[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    const double* src = grows + col;
+    unsigned r = 0;
+    for (; r + 7 < ngroups; r += 8) {
+#pragma unroll
+      for (int u = 0; u < 8; u++) p[u] += __ldcg(src + (size_t)(r + u) * kRowLen);
     }
-    if (threadIdx.x == 0) {
-      if (A.packed) A.packed[2 * M.obs_dim] = (double)A.num_envs;
-      *A.cta_ticket = 0u;
+    for (; r < ngroups; r++) p[0] += __ldcg(src + (size_t)r * kRowLen);
+    const double tot = ((p[0] + p[1]) + (p[2] + p[3])) + ((p[4] + p[5]) + (p[6] + p[7]));
+    if (col < kRowStats) {
+      if (A.packed) {
+        // packed layout of the VecNormalize kernels: [ sum obs[D], sumsq obs[D], n, sum ret, sumsq ret ]
+        const int D = M.obs_dim;
+        A.packed[col < 2 * D ? col : col + 1] = tot;
+      }
+    } else {
+      A.stats[col - kRowStats] += tot;
     }
+  }
+  if (threadIdx.x == 0) {
+    if (A.packed) A.packed[2 * M.obs_dim] = (double)A.num_envs;
+    *A.cta_ticket = 0u;
   }
 }
 

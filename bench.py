@@ -285,6 +285,8 @@ def main():
                          "(opt-in amortisation; 1 = SB3 semantics, the headline setting)")
     ap.add_argument("--host-outputs", choices=["mapped", "copy"], default="mapped",
                     help="numpy API: kernels write the outputs into mapped pinned host memory, or one D2H copy per step")
+    ap.add_argument("--pre-warmup", type=int, default=1500,
+                    help="untimed steps before the W warm-up steps of the headline leg (clock / power-state ramp)")
     ap.add_argument("--no-extra", action="store_true", help="skip the time-bounded legs for BASELINE.json configs[2] / [3]")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -347,7 +349,7 @@ def main():
             # headline leg on a box that may just have been idle: ~0.4 s of untimed steps so that clocks / power state
             # are up before the W warm-up steps (a cold box ran the first 200 steps 5 % slower; fixed count, every rank
             # takes part in each step's exchange)
-            for k in range(1500):
+            for k in range(args.pre_warmup):
                 vn.step_tensor(ring[k % 64])
         for k in range(warmup):
             vn.step_tensor(ring[k % 64])
@@ -474,7 +476,7 @@ def main():
                        "envs_per_gpu": n, "integrator": args.integrator, "frame_skip": head["frame_skip"],
                        "parallelism": f"env-sharded x{world}", "statistics_exchange": head["exchange"],
                        "stats_sync_every": args.stats_sync_every,
-                       "pre_warmup": "1500 untimed steps before the W warm-up steps (clock / power-state ramp)",
+                       "pre_warmup": "%d untimed steps before the W warm-up steps (clock / power-state ramp)" % args.pre_warmup,
                        "l2": "value / value_serialized: the persistent env state (%.1f MB) is re-read every step as in "
                              "a real rollout; value_l2_flushed: every step re-timed alone after a 192 MB L2 flush"
                              % (n * 720 / 1e6),

@@ -12,6 +12,9 @@
 
 #include "../../include/drloco_b200.h"
 #include "dev_model.h"
+#ifndef DRL_STEP_MAX_BLOCK
+#define DRL_STEP_MAX_BLOCK 128
+#endif
 
 namespace drl {
 size_t step_smem_bytes(int G, int envs_per_block);
@@ -355,7 +358,7 @@ extern "C" int drl_upload_model(DrlEnv* e, const DrlWalkerModel* m) {
   DeviceGuard guard__(c.device);
   {
     const int b = env_int("DRLOCO_B200_BLOCK", 0);     // developer hook: CTA size of the step kernel
-    if (b == 32 || b == 64 || b == 96 || b == 128) e->block = b;
+    if (b == 32 || b == 64 || b == 96 || b == 128 || (b == 256 && DRL_STEP_MAX_BLOCK >= 256)) e->block = b;
   }
   const size_t N = (size_t)c.num_envs;
   if (!e->d_model) {

@@ -319,8 +319,13 @@ __device__ __noinline__ void reset_env(const DevModel& M, const StepArgs& A, ES&
   __syncwarp();
 }
 
+// developer build switch (-DDRL_STEP_MAX_BLOCK=256): largest CTA the step kernel may be launched with; the shipped
+// library is built for 128-thread CTAs, four per SM
+#ifndef DRL_STEP_MAX_BLOCK
+#define DRL_STEP_MAX_BLOCK 128
+#endif
 template <int NV, int G, bool RK4, bool DBG>
-__global__ void __launch_bounds__(128, 4) mimic_step_kernel(const StepArgs A, const int do_reset_only) {
+__global__ void __launch_bounds__(DRL_STEP_MAX_BLOCK, 512 / DRL_STEP_MAX_BLOCK) mimic_step_kernel(const StepArgs A, const int do_reset_only) {
   using ES = EnvSmem<G>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   DevModel& M = *reinterpret_cast<DevModel*>(smem_raw);

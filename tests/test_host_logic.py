@@ -111,3 +111,44 @@ def test_speed_profile_and_oracle_speed_control():
     assert obs[1] == env.desired_walking_speed_trajectory[0]            # _get_obs runs before ep_dur += 1
     obs = env.step(np.zeros(8, np.float32))[0]
     assert obs[1] == env.desired_walking_speed_trajectory[1]
+
+
+def test_lazy_infos_behaves_like_a_list_of_dicts():
+    """infos of VecEnv.step (SB3 VecEnv contract: one dict per env, 'terminal_observation' for finished ones)."""
+    from drloco_b200.vec_env import LazyInfos
+    t = np.arange(3, dtype=np.float32)
+    infos = LazyInfos(5, {3: {"terminal_observation": t}})
+    assert len(infos) == 5 and infos[0] == {} and infos[-2]["terminal_observation"] is t
+    assert infos[0] is infos[0] and infos[0] is not infos[1]          # remembered once touched, never shared
+    infos[1]["episode"] = {"r": 1.0}
+    assert [sorted(d) for d in infos] == [[], ["episode"], [], ["terminal_observation"], []]
+    assert infos[1:3] == [{"episode": {"r": 1.0}}, {}]
+    assert infos == [{}, {"episode": {"r": 1.0}}, {}, {"terminal_observation": t}, {}]
+    with pytest.raises(IndexError):
+        infos[5]
+    with pytest.raises(IndexError):
+        infos[-6]
+    assert "3" in repr(infos)
+
+
+def test_terminal_record_buffer_is_parsed_into_infos():
+    """layout written by csrc/vecnorm.cu::vecnorm_terminal_compact_kernel: 4 header words (count first), then one record
+    { env index as int32 bits, d floats } per finished environment, in arbitrary order."""
+    import torch
+    from drloco_b200.vec_env import _TerminalRows
+    n, d = 6, 3
+    words = torch.zeros(_TerminalRows.words_for(n, d))
+    tr = _TerminalRows(n, d, "cpu", host_words=words)
+    assert tr.direct and tr.words == 4 + n * (d + 1)
+    assert tr.collect(np.float32) == {}
+    wi = words.numpy().view(np.int32)
+    wf = words.numpy()
+    wi[0] = 2
+    wi[4], wf[5:8] = 4, [1.0, 2.0, 3.0]
+    wi[8], wf[9:12] = 1, [-1.0, -2.0, -3.0]
+    got = tr.collect(np.float32)
+    assert sorted(got) == [1, 4]
+    np.testing.assert_array_equal(got[4]["terminal_observation"], [1.0, 2.0, 3.0])
+    np.testing.assert_array_equal(got[1]["terminal_observation"], [-1.0, -2.0, -3.0])
+    wf[9] = 99.0                                   # the rows handed out are copies, not views of the reused buffer
+    assert got[1]["terminal_observation"][0] == -1.0

@@ -201,9 +201,11 @@ def install_stubs():
     sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
 
 
-def load_reference(hypers_subst=()):
+def load_reference(hypers_subst=(), mimic_env_subst=()):
     """import the reference package with the two forced substitutions; returns (env class, Monitor class, utils).
-    ``hypers_subst``: textual edits of drloco/config/hypers.py (settings the reference expects its user to edit)."""
+    ``hypers_subst``: textual edits of drloco/config/hypers.py (settings the reference expects its user to edit).
+    ``mimic_env_subst``: textual edits of drloco/mujoco/mimic_env.py (only tools/gen_golden.py's speed-control fixture
+    uses it, for the one token without which that path raises; every other run loads the file as it is)."""
     sys.path.insert(0, REF)
     # is_remote() <=> 'code/torch' in cwd: no viewer, n_envs = 8 (Q12/Q13)
     work = os.path.join(tempfile.mkdtemp(), "code", "torch")
@@ -223,6 +225,9 @@ def load_reference(hypers_subst=()):
     sys.modules[name] = mod
     exec(compile(src, path, "exec"), mod.__dict__)
     setattr(sys.modules["drloco.ref_trajecs"], "straight_walk_trajecs", mod)
+    if mimic_env_subst:
+        import drloco.mujoco  # noqa: F401
+        _load_module_with("drloco.mujoco.mimic_env", "drloco/mujoco/mimic_env.py", list(mimic_env_subst))
     from drloco.mujoco.mimic_walker3d import MimicWalker3dEnv
     from drloco.mujoco.monitor_wrapper import Monitor
     from drloco.common import utils

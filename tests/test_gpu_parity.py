@@ -239,6 +239,34 @@ def test_eval_mode_golden_from_reference_python(golden_dir):
     env.close()
 
 
+def test_speed_control_golden_from_reference_python(golden_dir):
+    """speed control against the fixture produced by the reference's own env (tools/gen_golden.py speed; the reference
+    loaded with the one token without which `_get_obs` raises, see the fixture's meta): deterministic init states, cursor
+    and the profile-driven desired-velocity observation for whole episodes, states and rewards over the first steps."""
+    g = np.load(os.path.join(golden_dir, "w3d_speed_control.npz"))
+    env = _env(W3D, 1)
+    args = g["profile_3_args"]
+    env.env_method("activate_speed_control", list(args[:-1]), float(args[-1]))
+    np.testing.assert_allclose(env.desired_walking_speed_trajectory, g["profile_3"], rtol=1e-7)
+    E = g["actions"].shape[0]
+    for k in range(E):
+        obs = env.reset()
+        assert _rel(obs, g["obs0"][k][None]) < 2e-5
+        qg, vg, cg = env.get_state()
+        np.testing.assert_array_equal(cg[0], g["cursor0"][k])
+        assert _rel(qg, g["qpos0"][k][None]) < 1e-6
+        for t in range(int(g["n_valid"][k])):
+            obs, rew, done, _ = env.step(g["actions"][k, t][None])
+            assert not done[0]
+            qg, vg, cg = env.get_state()
+            np.testing.assert_array_equal(cg[0], g["cursor"][k, t])
+            assert abs(obs[0, 1] - g["obs"][k, t, 1]) < 1e-6
+            if t < 6:
+                assert _rel(obs, g["obs"][k, t][None]) < REL_TOL and abs(rew[0] - g["rew"][k, t]) < REL_TOL
+                assert _rel(qg, g["qpos"][k, t][None]) < REL_TOL
+    env.close()
+
+
 def test_long_horizon_divergence_is_reported():
     """beyond the short horizon fp32 and fp64 trajectories separate at contact events; termination decisions must
     still agree for as long as the states do."""

@@ -159,6 +159,46 @@ def test_eval_mode_matches_reference(spec, golden_dir):
     assert g["cursor0"][1, 0] == 1 and g["phase"][1, 0] == (g["cursor"][1, 0, 1]) / spec.mocap.step_len[0]
 
 
+def test_speed_control_matches_reference(spec, golden_dir):
+    """MimicEnv.activate_speed_control (mimic_env.py:298-327): profile generation, the desired-velocity observation
+    driven by it (:406-408, index ep_dur % len) and the deterministic initial states it implies (:536-537).  As shipped the
+    reference raises in _get_obs (scalar splat, :429) - recorded in the fixture; the rollouts come from the reference
+    loaded with that one token wrapped in np.atleast_1d (tools/gen_golden.py::gen_w3d_speed_control)."""
+    from drloco_b200.walkers import speed_profile
+    from oracle.env_oracle import OracleMimicEnv
+    g = np.load(os.path.join(golden_dir, "w3d_speed_control.npz"))
+    assert str(g["as_shipped_error"]).startswith("TypeError")
+    env = OracleMimicEnv(spec, OraclePhysics(spec.model))
+    i = 0
+    while "profile_%d" % i in g.files:
+        args = g["profile_%d_args" % i]
+        speeds, dur = list(args[:-1]), args[-1]
+        dur = int(dur) if dur == int(dur) else float(dur)
+        env.activate_speed_control(speeds, dur)
+        np.testing.assert_array_equal(env.desired_walking_speed_trajectory, g["profile_%d" % i])
+        np.testing.assert_array_equal(speed_profile(speeds, dur, spec.cfg.ctrl_freq), g["profile_%d" % i])   # host side of the GPU env
+        i += 1
+    assert i == 4 and len(env.desired_walking_speed_trajectory) == 50     # the last profile stays active
+    env.refs.count_steps_same_vel = int(g["count_at_construction"])    # after the construction-time step (Q14)
+    E = g["actions"].shape[0]
+    wrapped = False
+    for k in range(E):
+        obs = env.reset()
+        np.testing.assert_array_equal(obs, g["obs0"][k], err_msg=f"episode {k}")
+        np.testing.assert_array_equal(env.qpos, g["qpos0"][k])
+        assert (env.refs.i_step, env.refs.pos, env.refs.count_steps_same_vel, env.ep_dur) == tuple(g["cursor0"][k])
+        for t in range(int(g["n_valid"][k])):
+            obs, rew, done, _ = env.step(g["actions"][k, t])
+            assert (env.refs.i_step, env.refs.pos, env.refs.count_steps_same_vel, env.ep_dur) == tuple(g["cursor"][k, t])
+            np.testing.assert_array_equal(obs, g["obs"][k, t], err_msg=f"episode {k} step {t}")
+            np.testing.assert_array_equal(env.qpos, g["qpos"][k, t])
+            assert rew == g["rew"][k, t] and done == bool(g["done"][k, t])
+            wrapped |= env.ep_dur > 50
+    assert wrapped                                                       # the profile index wrapped around (ep_dur % len)
+    # obs[1] is the profile entry at ep_dur before the step's increment (mimic_env.py:97,100; mirroring leaves slot 1 alone)
+    np.testing.assert_array_equal(g["obs"][0, :60, 1], g["profile_3"][np.arange(60) % 50])
+
+
 def test_blowup_path_matches_reference(spec, golden_dir):
     """MujocoException path (mimic_env.py:82-91, Q19): reset inside step(), reward 0, done, then the VecEnv's own
     reset.  Same `random` seeding protocol as tools/gen_golden.py (gen_w3d_blowup)."""

@@ -376,8 +376,85 @@ def gen_w3d_cursor(out="w3d_cursor.npz", seed=0, n=1200):
     print(out, tr[0], tr[-1])
 
 
+SPEED_SPLAT = ("*self.desired_walking_speed,", "*np.atleast_1d(self.desired_walking_speed),")
+
+
+def gen_w3d_speed_control(out="w3d_speed_control.npz", seed=0, n_episodes=3, n_steps=70):
+    """MimicEnv.activate_speed_control (mimic_env.py:298-327): the generated profile, and rollouts with the profile
+    driving the desired-velocity observation (:406-408) from deterministic initial states (:536-537).
+
+    As shipped the path cannot produce an observation: `_get_obs` splats the profile's scalar entry
+    (`*self.desired_walking_speed`, :429) and raises TypeError.  `mode == "as_shipped"` records exactly that (message in
+    the fixture); `mode == "patched"` (own process) loads mimic_env.py with the one token wrapped in np.atleast_1d - the
+    evident intent, a 1-vector like the mocap branch returns - and records the rollouts."""
+    mode = os.environ.get("SPEED_MODE", "patched")
+    if mode == "as_shipped":
+        Env, Monitor, utils = load_reference()
+        e = Env()
+        e.activate_speed_control([0.5, 1.0, 0.75], 4)
+        try:
+            e.reset()
+            msg = "no error"
+        except TypeError as ex:
+            msg = "TypeError: %s" % ex
+        print("as shipped:", msg)
+        return msg
+    Env, Monitor, utils = load_reference(mimic_env_subst=[SPEED_SPLAT])
+    random.seed(seed)
+    np.random.seed(seed)
+    rng = np.random.default_rng(seed)
+    e = Env()
+    pristine = copy.deepcopy(e.refs.data)
+    count0 = e.refs.count_steps_same_vel
+    g = {}
+    cases = [([0.5, 1.0, 0.75], 4), ([1.0, 1.0], 10), ([0, 1, 2, 3], 1), ([0.6, 1.2, 0.9], 0.25)]
+    for i, (speeds, dur) in enumerate(cases):
+        e.activate_speed_control(speeds, dur)
+        g["profile_%d" % i] = np.asarray(e.desired_walking_speed_trajectory, np.float64)
+        g["profile_%d_args" % i] = np.array(list(speeds) + [dur], np.float64)
+    # the last profile (50 control steps) stays active: the rollouts wrap around it (ep_dur % len)
+    nv, nu, D = 14, 8, 29
+    E, T = n_episodes, n_steps
+    g.update(actions=np.zeros((E, T, nu), np.float32), obs=np.full((E, T, D), np.nan), rew=np.full((E, T), np.nan),
+             done=np.zeros((E, T), np.uint8), qpos=np.full((E, T, nv), np.nan),
+             cursor=np.full((E, T, 4), -1, np.int32), obs0=np.zeros((E, D)), qpos0=np.zeros((E, nv)),
+             cursor0=np.zeros((E, 4), np.int32), n_valid=np.zeros(E, np.int32))
+    for k in range(E):
+        e.refs.data = copy.deepcopy(pristine)                   # Q4 waiver
+        g["obs0"][k] = e.reset()
+        g["qpos0"][k] = e.sim.data.qpos
+        g["cursor0"][k] = (e.refs._i_step, e.refs._pos, e.refs.count_steps_same_vel, e.ep_dur)
+        for t in range(T):
+            a = (0.1 * rng.uniform(-1, 1, nu)).astype(np.float32)
+            g["actions"][k, t] = a
+            o, r, d, _ = e.step(a)
+            g["obs"][k, t], g["rew"][k, t], g["done"][k, t] = o, r, d
+            g["qpos"][k, t] = e.sim.data.qpos
+            g["cursor"][k, t] = (e.refs._i_step, e.refs._pos, e.refs.count_steps_same_vel, e.ep_dur)
+            g["n_valid"][k] = t + 1
+            if d:
+                break
+    g["count_at_construction"] = np.int32(count0)
+    g["as_shipped_error"] = np.array(os.environ.get("SPEED_AS_SHIPPED", ""))
+    g["meta"] = np.array("reference MimicWalker3dEnv over oracle physics with activate_speed_control; mimic_env.py loaded "
+                         "with %r -> %r (as shipped the observation raises, see as_shipped_error); Q4 waived; seed=%d"
+                         % (SPEED_SPLAT[0], SPEED_SPLAT[1], seed))
+    np.savez_compressed(os.path.join(REPO, "tests/golden", out), **g)
+    print(out, "valid steps per episode:", g["n_valid"], "profile lengths:",
+          [len(g["profile_%d" % i]) for i in range(len(cases))])
+
+
 if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
+    if which == "speed":                     # separate processes: one module substitution in the second
+        import subprocess
+        env = dict(os.environ, SPEED_MODE="as_shipped")
+        msg = subprocess.run([sys.executable, __file__, "speed_worker"], env=env, capture_output=True, text=True)
+        line = [x for x in msg.stdout.splitlines() if x.startswith("as shipped:")][0][len("as shipped: "):]
+        env = dict(os.environ, SPEED_MODE="patched", SPEED_AS_SHIPPED=line)
+        subprocess.check_call([sys.executable, __file__, "speed_worker"], env=env)
+    if which == "speed_worker":
+        gen_w3d_speed_control()
     if which in ("all", "cursor"):
         gen_w3d_cursor()
     if which in ("all", "rollout"):

@@ -4,6 +4,7 @@ import json
 import os
 
 import numpy as np
+import pytest
 
 from drloco_b200.config import EnvConfig
 from drloco_b200.training_monitor import (EVAL_INTERVAL_FREQUENT, EVAL_INTERVAL_MOST_FREQUENT, EVAL_INTERVAL_RARE,
@@ -133,3 +134,93 @@ def test_jsonl_writer_histogram(tmp_path):
     w.close()
     r = _records(str(tmp_path / "x" / "log.jsonl"))
     assert r[0] == {"tag": "a", "value": 1.5, "step": 7} and r[1]["counts"] == [1, 2, 1] and r[2]["counts"] == []
+
+
+class _RecordingWriter:
+    """collects what the monitor logs in the shape tools/gen_callback_golden.py records the reference's tensorboard /
+    wandb calls"""
+
+    def __init__(self):
+        self.events = []
+
+    def add_scalar(self, tag, value, step):
+        self.events.append(dict(kind="scalar", tag=tag, value=float(value), step=int(step)))
+
+    def add_histogram(self, tag, values, step, bins=40):
+        counts, edges = np.histogram(values, bins=bins)
+        self.events.append(dict(kind="hist", tag=tag, counts=[int(c) for c in counts], edges=[float(e) for e in edges],
+                                step=int(step)))
+
+    def flush(self):
+        pass
+
+    def close(self):
+        pass
+
+
+def test_trace_matches_the_reference_callback(tmp_path):
+    """tests/golden/callback_trace.json was produced by the reference's own TrainingMonitor (drloco/common/callback.py,
+    unmodified) over scripted env / policy objects (tools/gen_callback_golden.py).  The same scenarios through this
+    package's TrainingMonitor must log the same tags and values at the same calls, keep / delete / rename the same
+    checkpoint files and end in the same bookkeeping state."""
+    golden = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "callback_trace.json")))
+    cfg = EnvConfig()
+    assert cfg.ep_dur_max == 3000 and cfg.ctrl_freq == 200
+    ret_scale = np.sqrt(golden["ret_var"] + 1e-8)
+    for sc in golden["scenarios"]:
+        sp = str(tmp_path / sc["name"]) + "/"
+        queue = [list(e) for e in sc["eval_episodes"]]
+        results = list(sc["eval_results"])
+
+        def evaluator(policy, env, n, queue=queue, results=results):
+            eps = queue.pop(0)
+            assert n == len(eps)                                        # 10 evaluation episodes up to 1M steps, then 20
+            # what the reference's evaluation loop (callback.py:292-311) derives from the scripted episodes: duration
+            # incl. the terminal step, mean of the un-normalised rewards of the non-terminal steps, distance read
+            # before the terminal step
+            return dict(moved_distances=results.pop(0)["moved_distances"], ep_durs=[e[0] for e in eps],
+                        mean_rewards=[float(np.mean([e[2] / ret_scale * ret_scale] * (e[0] - 1))) for e in eps])
+        model = _Model()
+        model.env.attrs.update(golden["train_attrs"])
+        model.env.attrs.update(sc["attr_overrides"])
+        writer = _RecordingWriter()
+        mon = TrainingMonitor(model, cfg, sp, writer=writer, evaluator=evaluator)
+        mon.on_training_start()
+        for i, (ts, call) in enumerate(zip(sc["timesteps"], sc["calls"])):
+            if i in sc["force_eval_calls"]:
+                mon.n_steps_after_eval = mon.eval_interval
+            mon.num_timesteps = ts - model.env.num_envs                  # SB3 sets num_timesteps; on_step() adds n_envs
+            n_before, evals_before = len(writer.events), len(queue)
+            assert mon.on_step() is True
+            where = f"{sc['name']} call {i}"
+            assert mon.num_timesteps == ts
+            assert len(writer.events) - n_before == call["n_events"], where
+            assert (len(queue) < evals_before) == call["evaluated"], where
+            assert mon.skipped_steps == call["skipped_steps"] and mon.eval_interval == call["eval_interval"], where
+            assert mon.n_steps_after_eval == call["n_steps_after_eval"], where
+            assert sorted(os.listdir(sp + "models")) == call["models"], where
+            assert sorted(os.listdir(sp + "envs")) == call["envs"], where
+            # ep_lens: the reference empties the list on every call inside `num_timesteps % 1e6 < 1000`; here once per
+            # crossed 1M boundary (deliberate, see on_step) - both have done so by the time the reference has
+            assert (model.env.cleared > 0) == (call["cleared"] > 0), where
+        mon.on_training_end()
+        assert not queue
+        assert len(writer.events) == len(sc["events"])
+        for got, want in zip(writer.events, sc["events"]):
+            assert got["tag"] == want["tag"], sc["name"]
+            if want["kind"] == "hist":
+                assert got["kind"] == "hist" and got["counts"] == want["counts"] and got["step"] == want["step"]
+                np.testing.assert_allclose(got["edges"], want["edges"], rtol=1e-12, atol=1e-12)
+            else:                                    # tensorboard scalar, or the one value the reference sends to wandb
+                assert got["kind"] == "scalar" and (want["step"] is None or got["step"] == want["step"])
+                assert got["value"] == pytest.approx(want["value"], rel=1e-12, abs=1e-15), (sc["name"], got["tag"])
+        for name, want in sc["final"].items():
+            got = getattr(mon, name)
+            if isinstance(want, (list, bool)):
+                assert got == want, (sc["name"], name)
+            else:
+                assert float(got) == pytest.approx(want, rel=1e-12, abs=1e-15), (sc["name"], name)
+        if "steps_to_convergence" in sc["wandb_summary"]:
+            assert mon.steps_to_convergence == sc["wandb_summary"]["steps_to_convergence"]
+        else:
+            assert mon.steps_to_convergence is None

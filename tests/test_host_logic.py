@@ -152,3 +152,24 @@ def test_terminal_record_buffer_is_parsed_into_infos():
     np.testing.assert_array_equal(got[1]["terminal_observation"], [-1.0, -2.0, -3.0])
     wf[9] = 99.0                                   # the rows handed out are copies, not views of the reused buffer
     assert got[1]["terminal_observation"][0] == -1.0
+
+
+def test_defaults_equal_the_reference_config_modules():
+    """tests/golden/ref_config.json holds the values of the reference's own config modules as imported
+    (tools/gen_golden.py config): EnvConfig / PPOConfig defaults must be those."""
+    import json
+    import os
+    from drloco_b200.ppo import PPOConfig
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "ref_config.json")))
+    c, p = cfgm.EnvConfig(), PPOConfig()
+    assert c.env_id == g["ENV_ID"] and c.ctrl_freq == g["CTRL_FREQ"] and cfgm.SIM_FREQS == g["sim_freqs"]
+    assert c.eval_n_times == g["EVAL_N_TIMES"] and c.min_stable_distance == g["MIN_STABLE_DISTANCE"]
+    assert "/".join(c.modifications) == g["modification"] and c.is_mod(cfgm.MOD_MIRR_POLICY) == g["mirr_py"]
+    assert list(c.rew_weights) == json.loads(g["rew_weights"]) and c.rew_scale == g["rew_scale"]
+    assert c.alive_bonus == g["alive_bonus"] and c.ep_dur_max == g["ep_dur_max"] and c.gamma == g["gamma"]
+    assert p.gamma == g["gamma"] and p.init_logstd == g["init_logstd"] and p.minibatch_size == g["minibatch_size"]
+    assert p.batch_size == g["batch_size"] and p.lr_start == g["lr_start"] and p.lr_final == g["lr_final"]
+    assert g["lr_scale"] == 1                                              # plain linear decay lr_start -> lr_final
+    assert p.total_steps == g["mio_samples"] * 10 ** 6 and list(p.hidden) == g["hid_layer_sizes"]
+    assert g["activation_fns"] == ["Tanh", "Tanh"]                         # ActorCritic's trunk
+    assert p.clip_range == g["cliprange"] and p.ent_coef == g["ent_coef"] and p.n_epochs == g["noptepochs"]

@@ -376,6 +376,27 @@ def gen_w3d_cursor(out="w3d_cursor.npz", seed=0, n=1200):
     print(out, tr[0], tr[-1])
 
 
+def gen_ref_config(out="ref_config.json"):
+    """the step-path and learner settings of the reference's own config modules (drloco/config/config.py, hypers.py,
+    drloco/mujoco/config.py), read from the imported modules: pins EnvConfig / PPOConfig defaults."""
+    import json
+    load_reference()
+    from drloco.config import config as cfgl
+    from drloco.config import hypers as h
+    from drloco.mujoco import config as mjc
+    g = dict(ENV_ID=cfgl.ENV_ID, CTRL_FREQ=cfgl.CTRL_FREQ, EVAL_N_TIMES=cfgl.EVAL_N_TIMES,
+             MIN_STABLE_DISTANCE=cfgl.MIN_STABLE_DISTANCE, sim_freqs=dict(mjc.sim_freqs),
+             modification=h.modification, mirr_py=bool(h.is_mod(h.MOD_MIRR_POLICY)),
+             rew_weights=str(h.rew_weights), rew_scale=h.rew_scale, alive_bonus=h.alive_bonus, ep_dur_max=h.ep_dur_max,
+             gamma=h.gamma, init_logstd=h.init_logstd, minibatch_size=h.minibatch_size, batch_size=h.batch_size,
+             lr_start=h.lr_start, lr_final=h.lr_final, lr_scale=h.lr_scale, mio_samples=h.mio_samples, n_envs=h.n_envs,
+             hid_layer_sizes=list(h.hid_layer_sizes), activation_fns=[f.__name__ for f in h.activation_fns],
+             cliprange=h.cliprange, ent_coef=h.ent_coef, noptepochs=h.noptepochs,
+             meta="values of the reference's config modules as imported under the stubs (is_remote() true)")
+    json.dump(g, open(os.path.join(REPO, "tests/golden", out), "w"), indent=1)
+    print(out, g)
+
+
 SPEED_SPLAT = ("*self.desired_walking_speed,", "*np.atleast_1d(self.desired_walking_speed),")
 
 
@@ -455,6 +476,8 @@ if __name__ == "__main__":
         subprocess.check_call([sys.executable, __file__, "speed_worker"], env=env)
     if which == "speed_worker":
         gen_w3d_speed_control()
+    if which == "config":
+        gen_ref_config()
     if which in ("all", "cursor"):
         gen_w3d_cursor()
     if which in ("all", "rollout"):

@@ -213,6 +213,30 @@ def test_w165_golden_rollout_from_reference_python(golden_dir):
     env.close()
 
 
+def test_w165_eval_mode_golden_from_reference_python(golden_dir):
+    """MimicWalker165cm65kgEnv in evaluation mode against the reference-generated fixture (tools/gen_golden.py
+    w165_eval): every episode starts at sample 0 of the recording (base_ref_trajecs.py:70-77); cursor for whole
+    episodes, states / observations / rewards over the first steps (the oracle's sensitivity probe flags none of them)."""
+    g = np.load(os.path.join(golden_dir, "w165_eval.npz"))
+    env = _env(W165, 1)
+    env.env_method("activate_evaluation")
+    for k in range(g["actions"].shape[0]):
+        obs = env.reset()
+        assert _rel(obs, g["obs0"][k][None]) < 2e-5
+        qg, vg, cg = env.get_state()
+        np.testing.assert_array_equal(cg[0, [1, 3]], g["cursor0"][k])
+        assert _rel(qg, g["qpos0"][k][None]) < 1e-6
+        for t in range(int(g["n_valid"][k])):
+            obs, rew, done, _ = env.step(g["actions"][k, t][None])
+            assert not done[0]
+            qg, vg, cg = env.get_state()
+            np.testing.assert_array_equal(cg[0, [1, 3]], g["cursor"][k, t])
+            if t < 5:
+                assert _rel(obs, g["obs"][k, t][None]) < REL_TOL and abs(rew[0] - g["rew"][k, t]) < REL_TOL
+                assert _rel(qg, g["qpos"][k, t][None]) < REL_TOL
+    env.close()
+
+
 def test_eval_mode_golden_from_reference_python(golden_dir):
     """evaluation mode against the fixture produced by the reference's own env (tools/gen_golden.py eval): deterministic
     init states incl. the reference's table aliasing (Q27) - cursor, phase, desired speed and mirroring for whole

@@ -159,6 +159,31 @@ def test_eval_mode_matches_reference(spec, golden_dir):
     assert g["cursor0"][1, 0] == 1 and g["phase"][1, 0] == (g["cursor"][1, 0, 1]) / spec.mocap.step_len[0]
 
 
+def test_w165_eval_mode_matches_reference(golden_dir):
+    """MimicWalker165cm65kgEnv in evaluation mode: every episode starts at sample 0 of the recording
+    (base_ref_trajecs.py:70-77 through mimic_env.py:536-537,575-579)."""
+    from drloco_b200.config import EnvConfig
+    from oracle.env_oracle import OracleMimicEnv
+    g = np.load(os.path.join(golden_dir, "w165_eval.npz"))
+    spec = make_spec(EnvConfig(env_id="MimicWalker165cm65kg"))
+    env = OracleMimicEnv(spec, OraclePhysics(spec.model))
+    env._EVAL_MODEL = True
+    E = g["actions"].shape[0]
+    for k in range(E):
+        obs = env.reset()
+        np.testing.assert_array_equal(obs, g["obs0"][k], err_msg=f"episode {k}")
+        np.testing.assert_array_equal(env.qpos, g["qpos0"][k])
+        assert (env.refs.pos, env.ep_dur) == tuple(g["cursor0"][k])
+        for t in range(int(g["n_valid"][k])):
+            obs, rew, done, _ = env.step(g["actions"][k, t])
+            assert (env.refs.pos, env.ep_dur) == tuple(g["cursor"][k, t])
+            np.testing.assert_array_equal(obs, g["obs"][k, t], err_msg=f"episode {k} step {t}")
+            np.testing.assert_array_equal(env.qpos, g["qpos"][k, t])
+            assert rew == g["rew"][k, t] and done == bool(g["done"][k, t])
+    np.testing.assert_array_equal(g["cursor0"][:, 0], g["cursor0"][0, 0])        # the same start every time
+    np.testing.assert_array_equal(g["obs0"][1], g["obs0"][0])
+
+
 def test_speed_control_matches_reference(spec, golden_dir):
     """MimicEnv.activate_speed_control (mimic_env.py:298-327): profile generation, the desired-velocity observation
     driven by it (:406-408, index ep_dur % len) and the deterministic initial states it implies (:536-537).  As shipped the

@@ -163,6 +163,50 @@ def gen_w165_rollout(n_envs=6, n_steps=160, seed=0, out="w165_rollout.npz"):
           int((np.diff(g["cursor"][:, :, 0], axis=0) < 0).sum()))
 
 
+def gen_w165_eval(out="w165_eval.npz", seed=0, n_episodes=3, n_steps=40):
+    """MimicWalker165cm65kgEnv in evaluation mode (mimic_env.py:245,536-537 -> base_ref_trajecs.py:70-77): every episode
+    starts at sample 0 of the recording.  Same synthetic recording and reference loading as gen_w165_rollout."""
+    import scipy.io as spio
+    from drloco_b200.ref_trajecs.loco3d_trajecs import synthetic_loco3d, N_ROWS
+    proj = tempfile.mkdtemp()
+    os.makedirs(os.path.join(proj, "mocaps/loco3d"))
+    ang, vel = synthetic_loco3d()
+    spio.savemat(os.path.join(proj, "mocaps/loco3d/loco3d_guoping.mat"),
+                 {"angJoi": ang, "angDJoi": vel, "rowNameIK": np.array([f"row{i}" for i in range(N_ROWS)], dtype=object)})
+    Env, Monitor, utils = load_reference_w165(proj)
+    random.seed(seed)
+    np.random.seed(seed)
+    rng = np.random.default_rng(seed)
+    e = Env()
+    pristine = e.refs._qpos_full.copy()
+    e.activate_evaluation()
+    nv, nu, D = 19, 13, 47
+    E, T = n_episodes, n_steps
+    g = dict(actions=np.zeros((E, T, nu), np.float32), obs=np.full((E, T, D), np.nan), rew=np.full((E, T), np.nan),
+             done=np.zeros((E, T), np.uint8), qpos=np.full((E, T, nv), np.nan), cursor=np.full((E, T, 2), -1, np.int32),
+             obs0=np.zeros((E, D)), qpos0=np.zeros((E, nv)), cursor0=np.zeros((E, 2), np.int32),
+             n_valid=np.zeros(E, np.int32))
+    for k in range(E):
+        e.refs._qpos_full[...] = pristine                        # Q4 waiver
+        g["obs0"][k] = e.reset()
+        g["qpos0"][k] = e.sim.data.qpos
+        g["cursor0"][k] = (e.refs._pos, e.ep_dur)
+        for t in range(T):
+            a = (0.1 * (k + 1) * rng.uniform(-1, 1, nu)).astype(np.float32)
+            g["actions"][k, t] = a
+            o, r, d, _ = e.step(a)
+            g["obs"][k, t], g["rew"][k, t], g["done"][k, t] = o, r, d
+            g["qpos"][k, t] = e.sim.data.qpos
+            g["cursor"][k, t] = (e.refs._pos, e.ep_dur)
+            g["n_valid"][k] = t + 1
+            if d:
+                break
+    g["meta"] = np.array("reference MimicWalker165cm65kgEnv (ENV_ID / mirroring set in the config) in evaluation mode over "
+                         "oracle physics on synthetic_loco3d(seed 0); Q4 waived; seed=%d" % seed)
+    np.savez_compressed(os.path.join(REPO, "tests/golden", out), **g)
+    print(out, "valid steps per episode:", g["n_valid"], "first cursors:", g["cursor0"].tolist())
+
+
 def gen_w3d_rollout(n_envs=8, n_steps=400, seed=0, out="w3d_rollout.npz", hypers_subst=()):
     Env, Monitor, utils = load_reference(hypers_subst)
     random.seed(seed)
@@ -491,3 +535,5 @@ if __name__ == "__main__":
                         hypers_subst=[("ep_dur_max = 3000", "ep_dur_max = 25")])
     if which == "w165":                      # separate process: the reference's config module is per-ENV_ID
         gen_w165_rollout()
+    if which == "w165_eval":
+        gen_w165_eval()
